@@ -1,0 +1,214 @@
+"""CPU suite (`-m "not gpu"`): the oracle against the reference's fixtures / published
+figures, the host logic, and that the C-ABI library loads and exports what the header says."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dnbc_scala_b200 import dataset
+from dnbc_scala_b200.scala_compat import improve, java_string_hash, scala_map_order
+from tests.util import GOLDEN, perturb, random_model, sample
+
+
+
+@pytest.fixture(scope="module")
+def answers():
+    with open(os.path.join(GOLDEN, "known_answers.json")) as fh:
+        return json.load(fh)
+
+
+# README.md:9-15 (65 / 42 / 76) and DynamicNaiveBayesianClassifierTest.scala:13,19,25 (>65, >40, >72)
+@pytest.mark.parametrize("name,published,threshold", [
+    ("robot_no_momentum", 65, 65), ("robot_no_momentum_continuous", 42, 40), ("robot_no_momentum_bivariate", 76, 72)])
+def test_oracle_reproduces_published_robot_accuracy(oracle, name, published, threshold):
+    ds = dataset.load(os.path.join(GOLDEN, name + ".data.gz"))
+    learn, test = oracle.Data.of(ds.learn), oracle.Data.of(ds.test)
+    m = oracle.mle(learn, ds.N, ds.V, None, flags=oracle.QUIRK_TRANSITIONS)
+    path, score, tie = oracle.decode(m, test, oracle.DECODE_REFERENCE)
+    acc = oracle.accuracy(test, path)
+    assert acc > threshold
+    assert int(acc) == published          # README rounds down to whole percent
+    # a true back-traced Viterbi is far better: the published figure needs the reference's quirks
+    bpath, _, _ = oracle.decode(m, test, oracle.DECODE_BACKTRACE)
+    assert oracle.accuracy(test, bpath) > acc + 5
+
+
+def test_oracle_gaussian_mixture_fixture(oracle):
+    """README.md:14-15 publishes 96 / 99 %; DNBCTest.scala:29-34 asserts rate1 + 0.03 < rate2."""
+    ds = dataset.load(os.path.join(GOLDEN, "gaussian_mixture.data.gz"))
+    learn, test = oracle.Data.of(ds.learn), oracle.Data.of(ds.test)
+    rates = {}
+    for k in (1, 2):
+        cen = None
+        if k == 2:
+            cen = {(0, j): [learn.cont[0, learn.labels == j].min(), learn.cont[0, learn.labels == j].max()]
+                   for j in range(ds.N)}
+        m = oracle.mle(learn, ds.N, ds.V, [k], flags=0, init_centroids=cen)
+        path, _, _ = oracle.decode(m, test, oracle.DECODE_REFERENCE)
+        rates[k] = oracle.accuracy(test, path)
+    assert int(rates[1]) == 96 and int(rates[2]) == 99
+    assert rates[1] + 0.03 < rates[2]
+    # as the code reads (transition quirk ON) the single training sequence degenerates A
+    mq = oracle.mle(learn, ds.N, ds.V, [1], flags=oracle.QUIRK_TRANSITIONS)
+    assert sorted(np.round(mq.A.flatten(), 12).tolist()) == [0.0, 0.0, 1.0, 1.0]
+
+
+def test_oracle_matches_committed_known_answers(oracle, answers):
+    for name, entry in answers.items():
+        ds = dataset.load(os.path.join(GOLDEN, name + ".data.gz"))
+        learn, test = oracle.Data.of(ds.learn), oracle.Data.of(ds.test)
+        for key, r in entry["runs"].items():
+            quirk, k = int(key[5]), int(key.split("_k")[1])
+            cen = None
+            if r["init_centroids"]:
+                cen = {tuple(int(x) for x in kk.split(",")): v for kk, v in r["init_centroids"].items()}
+            m = oracle.mle(learn, ds.N, ds.V, [k] if learn.C else None,
+                           flags=oracle.QUIRK_TRANSITIONS if quirk else 0, init_centroids=cen)
+            path, _, _ = oracle.decode(m, test, oracle.DECODE_REFERENCE)
+            assert abs(oracle.accuracy(test, path) - r["accuracy_reference"]) < 1e-9
+            np.testing.assert_allclose(m.mu.ravel(), np.array(r["mu"]).ravel(), rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(m.var.ravel(), np.array(r["var"]).ravel(), rtol=1e-12, atol=1e-12)
+
+
+def test_k1_mixture_is_closed_form(oracle):
+    """EM1D.java:36-54: k = 1 gives mean / population variance / weight 1 and EM leaves it unchanged."""
+    rng = np.random.default_rng(0)
+    x = rng.normal(3, 2, 500)
+    assign, cen, its = oracle.kmeans_1d(x, [x[7]])
+    assert its == 1 and (assign == 0).all()
+    w, mu, var = oracle.em1d_initialize(x, 1, assign)
+    assert w[0] == 1.0 and abs(mu[0] - x.mean()) < 1e-12 and abs(var[0] - x.var()) < 1e-12
+    w2, mu2, var2, ll = oracle.em1d_run(x, w, mu, var)
+    assert len(ll) == 2 and abs(mu2[0] - mu[0]) < 1e-12 and abs(var2[0] - var[0]) < 1e-10
+
+
+def test_density_forms_agree(oracle):
+    """jMEF UnivariateGaussian.density (:197) and the 1x1 MLlib pdf are the same function."""
+    L = oracle.lib()
+    for x, mu, var in [(0.3, -1.0, 2.5), (10.0, 9.0, 0.01), (-4.0, 5.0, 16.0)]:
+        a, b = L.orc_jmef_density(x, mu, var), L.orc_mllib_pdf(x, mu, var)
+        ref = np.exp(-(x - mu) ** 2 / (2 * var)) / np.sqrt(2 * np.pi * var)
+        assert abs(a - ref) <= 1e-15 * max(1, ref) and abs(b - ref) <= 4e-16 * max(1, ref) + 1e-300 or abs(a - b) < 1e-12 * ref
+
+
+def test_bridge_clamped_estep_equals_supervised_counts(oracle):
+    """with every label clamped gamma/xi are one-hot, so the E-step statistics are
+    the reference's counts (DNBC.scala:163-220) and the M-step its normalisation (Edge.scala:53-59)."""
+    m = random_model(oracle, 6, [4, 3], [2], 1)
+    data = sample(oracle, m, [30, 1, 17, 25, 2], 2)
+    cnt_pi, cnt_A, cnt_B = oracle.mle_counts(m.N, m.Vmax, data, 0)
+    q = perturb(oracle, m, 3)
+    st = oracle.split_stats(q, oracle.estep(q, data, clamp_labels=True))
+    np.testing.assert_allclose(st["pi"], cnt_pi, atol=1e-9)
+    np.testing.assert_allclose(st["xi"], cnt_A, atol=1e-9)
+    np.testing.assert_allclose(st["cat"], cnt_B, atol=1e-9)
+    # iterating the clamped GMM M-step reproduces EM1D.run's series from the same initial mixture
+    j, c = 2, 0
+    x = oracle.edge_points(data, c, j)
+    w0, mu0, var0 = q.w[c, j, :2].copy(), q.mu[c, j, :2].copy(), q.var[c, j, :2].copy()
+    w_ref, mu_ref, var_ref, ll = oracle.em1d_run(x, w0, mu0, var0, max_iters=3, rel_tol=0.0)
+    qq = q.copy()
+    for _ in range(3):
+        oracle.mstep(qq, oracle.estep(qq, data, clamp_labels=True), data.S)
+    np.testing.assert_allclose(qq.mu[c, j, :2], mu_ref, rtol=1e-9)
+    np.testing.assert_allclose(qq.var[c, j, :2], var_ref, rtol=1e-8)
+    np.testing.assert_allclose(qq.w[c, j, :2], w_ref, rtol=1e-9)
+
+
+def test_em_loglik_is_monotone_and_rows_normalised(oracle):
+    m = random_model(oracle, 5, [6], [2, 1], 4)
+    data = sample(oracle, m, [40] * 30, 5)
+    q = perturb(oracle, m, 6)
+    ll = oracle.em_iterate(q, data, 6)
+    assert (np.diff(ll) > -1e-7 * abs(ll[0])).all()
+    np.testing.assert_allclose(q.A.sum(1), 1, atol=1e-12)
+    np.testing.assert_allclose(q.pi.sum(), 1, atol=1e-12)
+    np.testing.assert_allclose(q.w.sum(-1), 1, atol=1e-12)
+    g = oracle.posteriors(q, data)
+    np.testing.assert_allclose(g.sum(1), 1, atol=1e-9)
+
+
+def test_reference_decode_quirks(oracle):
+    """T == 1 scores 0.0 (DNBC.scala:90, vcur stays empty); ties go to the first state."""
+    m = random_model(oracle, 3, [2], [], 7)
+    m.pi[:] = 1 / 3
+    m.B[0, :, :] = 0.5
+    data = oracle.Data([0, 1, 4], np.zeros((1, 4), np.uint8), np.zeros((0, 4)), np.zeros(4, np.int32))
+    path, score, tie = oracle.decode(m, data, oracle.DECODE_REFERENCE)
+    assert score[0] == 0.0 and path[0] == 0 and tie[0] & 1
+
+
+def test_dataset_roundtrip(tmp_path):
+    ds = dataset.load(os.path.join(GOLDEN, "robot_no_momentum_bivariate.data.gz"))
+    assert ds.types == ["continuous", "discrete"] and ds.N == 12 and ds.V == [4]
+    assert ds.learn.S == 200 and ds.test.S == 200 and ds.learn.P == 40000
+    sub = ds.learn.select(range(5))
+    p = tmp_path / "x.data"
+    dataset.write(str(p), ds.types, ds.vocab, sub, ds.test.select(range(2)))
+    back = dataset.load(str(p))
+    assert back.learn.S == 5 and back.test.S == 2
+    np.testing.assert_array_equal(back.learn.cont, sub.cont)
+    assert [back.vocab.states[i] for i in back.learn.labels] == [ds.vocab.states[i] for i in sub.labels]
+    with pytest.raises(ValueError, match="Number of observed variables is inconsistent"):
+        dataset.parse_lines(["discrete discrete", "a 1", "b 1 2"])
+
+
+def test_scala_map_order():
+    assert java_string_hash("h0") == 3272 and java_string_hash("") == 0
+    assert java_string_hash("3:3") == ((51 * 31 + 58) * 31 + 51)
+    assert scala_map_order(["b", "a", "c", "a"]) == ["b", "a", "c"]          # Map1-4: insertion order
+    keys = [f"h{i}" for i in range(10)]
+    order = scala_map_order(keys)
+    assert sorted(order) == sorted(keys) and order != keys
+    assert order == sorted(keys, key=lambda k: tuple((improve(java_string_hash(k)) >> (5 * l)) & 31 for l in range(7)))
+
+
+def test_library_exports_every_header_symbol():
+    from dnbc_scala_b200 import _native as nat
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "dnbc_b200.h")).read()
+    declared = set(re.findall(r"\b(dnbc_[a-z0-9_]+)\s*\(", hdr)) - {"dnbc_ctx"}
+    assert declared == set(nat.SYMBOLS)
+    L = ctypes.CDLL(nat.LIB_PATH)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert nat.lib().dnbc_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product refuses to run (no oracle / CPU path behind the API)."""
+    import torch
+    from dnbc_scala_b200 import _native as nat
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nat.DnbcError) as ei:
+        nat.Context(3, [2], [1])
+    assert ei.value.code == nat.ENODEVICE and "no CPU path" in str(ei.value)
+
+
+def test_host_mirror_argument_errors():
+    """DynamicNaiveBayesianClassifierTest.scala:36-53 -- the checks that fire before any device work."""
+    from dnbc_scala_b200 import DynamicNaiveBayesianClassifier as DNBC, ObservedState, State
+    valid = ObservedState(["b"], [1.1])
+    invalid = ObservedState(["b", "c"], [1.1])
+    first = State("A", ObservedState(["r"], [42.666]))
+    valid_seq, invalid_seq = [first, State("B", valid)], [first, State("B", invalid)]
+    with pytest.raises(Exception, match="at least one"):
+        DNBC.mle([valid_seq], [0])
+    with pytest.raises(Exception, match="does not correspond"):
+        DNBC.mle([valid_seq], [1, 2])
+    with pytest.raises(Exception, match="Number of observed variables is inconsistent"):
+        DNBC.mle([invalid_seq])
+
+
+def test_product_never_imports_the_oracle():
+    """The product path may mention the oracle in comments but never loads, links or includes it."""
+    pkg = os.path.join(os.path.dirname(GOLDEN), "..", "dnbc_scala_b200")
+    pat = re.compile(r"^\s*(import oracle|from oracle|from \.\.? ?oracle|#include .*oracle)|libdnbc_oracle|CDLL\(.*oracle", re.M)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                src = open(os.path.join(root, f)).read()
+                assert not pat.search(src), f

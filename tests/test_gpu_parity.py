@@ -1,0 +1,388 @@
+"""GPU parity tests (`-m gpu`): the CUDA path through the C ABI against the fp64 oracle on
+the same seeded inputs and on the reference's own fixtures (tests/golden/)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from dnbc_scala_b200 import _native as nat
+from dnbc_scala_b200 import dataset
+from tests.util import GOLDEN, ctx_for, perturb, random_model, sample, upload
+
+pytestmark = pytest.mark.gpu
+
+# north_star: learned parameters and per-iteration log-likelihood within ~1e-5 relative
+TOL = 1e-5
+
+
+def _fixture(oracle, name):
+    ds = dataset.load(os.path.join(GOLDEN, name + ".data.gz"))
+    return ds, oracle.Data.of(ds.learn), oracle.Data.of(ds.test)
+
+
+def _assert_params(ctx, m, rtol=TOL, atol=1e-9):
+    p = ctx.get_params()
+    np.testing.assert_allclose(p["pi"], m.pi, rtol=rtol, atol=atol)
+    np.testing.assert_allclose(p["A"], m.A, rtol=rtol, atol=atol)
+    np.testing.assert_allclose(p["B"], m.B, rtol=rtol, atol=atol)
+    for c in range(m.C):
+        k = int(m.K[c])
+        np.testing.assert_allclose(p["w"][c, :, :k], m.w[c, :, :k], rtol=rtol, atol=atol)
+        np.testing.assert_allclose(p["mu"][c, :, :k], m.mu[c, :, :k], rtol=rtol, atol=1e-6)
+        np.testing.assert_allclose(p["var"][c, :, :k], m.var[c, :, :k], rtol=rtol, atol=1e-6)
+
+
+def _paths_equal_except_ties(path, opath, tie, otie, off):
+    """Paths identical except at steps either side flagged as tied (north_star)."""
+    diff = np.nonzero(path.astype(np.int64) != opath.astype(np.int64))[0]
+    if len(diff) == 0:
+        return 0
+    flagged = (tie | otie) != 0
+    # a tie at step t may also change later steps of the same sequence (different delta carried on)
+    seq_of = np.searchsorted(off, diff, side="right") - 1
+    for n, s in zip(diff, seq_of):
+        assert flagged[off[s]:n + 1].any(), f"unflagged path difference at point {n}"
+    return len(diff)
+
+
+# ---------------------------------------------------------------------------------
+# supervised learner (rows a3-a13)
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["robot_no_momentum", "robot_no_momentum_bivariate", "gaussian_mixture"])
+@pytest.mark.parametrize("flags", [0, 1, 2, 3])
+def test_supervised_counts_bit_exact(oracle, name, flags):
+    ds, learn, _ = _fixture(oracle, name)
+    want = oracle.mle_counts(ds.N, max([1] + ds.V), learn, flags)
+    with nat.Context(ds.N, ds.V, [1] * learn.C) as ctx:
+        upload(ctx, learn)
+        got = ctx.supervised_counts(flags)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+
+
+@pytest.mark.parametrize("name", ["robot_no_momentum", "robot_no_momentum_continuous", "robot_no_momentum_bivariate"])
+def test_mle_k1_matches_oracle_on_fixtures(oracle, name):
+    ds, learn, _ = _fixture(oracle, name)
+    m = oracle.mle(learn, ds.N, ds.V, None, flags=oracle.QUIRK_TRANSITIONS)
+    with nat.Context(ds.N, ds.V, [1] * learn.C) as ctx:
+        upload(ctx, learn)
+        ctx.mle(nat.QUIRK_TRANSITIONS)
+        _assert_params(ctx, m, rtol=1e-9)
+        np.testing.assert_array_equal(ctx.get_params()["active"], m.active)
+
+
+def test_mle_k2_with_injected_centroids(oracle):
+    """gaussian_mixture.data with hint 2 (DNBCTest.scala:29-34), same initial centroids on both sides."""
+    ds, learn, test = _fixture(oracle, "gaussian_mixture")
+    cen = {(0, j): [learn.cont[0, learn.labels == j].min(), learn.cont[0, learn.labels == j].max()] for j in range(ds.N)}
+    trace = []
+    m = oracle.mle(learn, ds.N, ds.V, [2], flags=0, init_centroids=cen, trace=trace)
+    dense = np.zeros((1, ds.N, 2))
+    for (c, j), v in cen.items():
+        dense[c, j] = v
+    with nat.Context(ds.N, ds.V, [2]) as ctx:
+        upload(ctx, learn)
+        ll, its = ctx.mle(0, dense)
+        _assert_params(ctx, m, rtol=1e-8)
+        for tr in trace:  # per-edge log-likelihood series of EM1D.run
+            n = len(tr.ll_series)
+            assert its[tr.c, tr.state] == n - 1
+            np.testing.assert_allclose(ll[tr.c, tr.state, :n], tr.ll_series, rtol=1e-9)
+        upload(ctx, test)
+        path, _, _ = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+        assert int(oracle.accuracy(test, path.astype(np.int32))) == 99   # README.md:15
+
+
+def test_mle_synthetic_mixtures_and_double_count(oracle):
+    m = random_model(oracle, 5, [7, 3], [3, 1, 2], 11)
+    data = sample(oracle, m, [50] * 40 + [1, 2, 3], 12)
+    rng = np.random.default_rng(13)
+    cen = {}
+    for c in range(m.C):
+        for j in range(m.N):
+            x = np.unique(oracle.edge_points(data, c, j))
+            cen[(c, j)] = rng.choice(x, size=int(m.K[c]), replace=False).tolist()
+    for flags in (0, 3):
+        want = oracle.mle(data, m.N, m.V, list(m.K), flags=flags, init_centroids=cen)
+        dense = np.zeros((m.C, m.N, m.Kmax))
+        for (c, j), v in cen.items():
+            dense[c, j, :len(v)] = v
+        with nat.Context(m.N, m.V, m.K) as ctx:
+            upload(ctx, data)
+            ctx.mle(flags, dense)
+            _assert_params(ctx, want, rtol=1e-7)
+
+
+# ---------------------------------------------------------------------------------
+# K1 emission
+# ---------------------------------------------------------------------------------
+def test_emission_f64_matches_reference_arithmetic(oracle):
+    ds, learn, test = _fixture(oracle, "robot_no_momentum_bivariate")
+    m = oracle.mle(learn, ds.N, ds.V, None, flags=oracle.QUIRK_TRANSITIONS)
+    want = oracle.emission_loglik(m, test)
+    with ctx_for(nat, m) as ctx:
+        upload(ctx, test, labels=False)
+        got = ctx.emission_logprob(nat.PREC_F64)
+        got32 = ctx.emission_logprob(nat.PREC_F32)
+    fin = np.isfinite(want)
+    assert (np.isfinite(got) == fin).all()
+    np.testing.assert_allclose(got[fin], want[fin], rtol=1e-13, atol=1e-13)
+    assert (np.isfinite(got32) == fin).all()
+    np.testing.assert_allclose(got32[fin], want[fin], rtol=2e-6, atol=2e-5)
+
+
+def test_emission_f32_config1_shape(oracle):
+    """README perf-set shape: N=10, D=5, C=5, K<=4, incl. an unseen symbol."""
+    m = random_model(oracle, 10, [10] * 5, [3, 1, 4, 2, 3], 21)
+    data = sample(oracle, m, [200] * 20, 22)
+    data.disc[2, 5] = 255       # never-seen symbol -> probability 0 -> -inf (Edge.scala:70-73)
+    want = oracle.emission_loglik(m, data)
+    with ctx_for(nat, m) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        got = ctx.emission_logprob(nat.PREC_F32)
+    assert np.isneginf(got[5]).all() and np.isneginf(want[5]).all()
+    fin = np.isfinite(want)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-5)
+
+
+# ---------------------------------------------------------------------------------
+# K5 decode
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["robot_no_momentum", "robot_no_momentum_continuous", "robot_no_momentum_bivariate"])
+def test_reference_decode_path_for_path_on_fixtures(oracle, name):
+    with open(os.path.join(GOLDEN, "known_answers.json")) as fh:
+        known = json.load(fh)[name]["runs"]
+    ds, learn, test = _fixture(oracle, name)
+    m = oracle.mle(learn, ds.N, ds.V, None, flags=oracle.QUIRK_TRANSITIONS)
+    opath, oscore, otie = oracle.decode(m, test, oracle.DECODE_REFERENCE)
+    with ctx_for(nat, m) as ctx:
+        upload(ctx, test, labels=False)
+        path, score, tie = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+        path32, score32, tie32 = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F32)
+    assert _paths_equal_except_ties(path, opath, tie, otie, test.off) == 0 or tie.any()
+    np.testing.assert_array_equal(tie, otie)
+    fin = np.isfinite(oscore)
+    np.testing.assert_allclose(score[fin], oscore[fin], rtol=1e-12)
+    acc = oracle.accuracy(test, path.astype(np.int32))
+    key = "quirk1_k1" if learn.C else "quirk1_k0"
+    assert abs(acc - known[key]["accuracy_reference"]) < 1e-9
+    # the fp32 throughput path may differ only where it flags a near-tie
+    ndiff = _paths_equal_except_ties(path32, opath, tie32, otie, test.off)
+    assert ndiff <= 0.002 * len(opath)
+    np.testing.assert_allclose(score32[fin], oscore[fin], rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,V,K", [(3, [4], []), (10, [10] * 5, [3, 1, 4, 2, 3]), (33, [5], [2]), (64, [6, 6], [2, 2])])
+def test_backtrace_decode_matches_oracle(oracle, N, V, K):
+    m = random_model(oracle, N, V, K, 31, transitions_per_state=min(N, 5))
+    data = sample(oracle, m, [60, 1, 2, 17] + [40] * 20, 32)
+    opath, oscore, otie = oracle.decode(m, data, oracle.DECODE_BACKTRACE)
+    rpath, rscore, rtie = oracle.decode(m, data, oracle.DECODE_REFERENCE)
+    with ctx_for(nat, m) as ctx:
+        upload(ctx, data, labels=False)
+        path, score, tie = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F64)
+        p32, s32, t32 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+        rp, rs, rt = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+    _paths_equal_except_ties(path, opath, tie, otie, data.off)
+    np.testing.assert_allclose(score, oscore, rtol=1e-12)
+    _paths_equal_except_ties(p32, opath, t32, otie, data.off)
+    np.testing.assert_allclose(s32, oscore, rtol=1e-5)
+    _paths_equal_except_ties(rp, rpath, rt, rtie, data.off)
+    fin = np.isfinite(rscore)
+    np.testing.assert_allclose(rs[fin], rscore[fin], rtol=1e-12)
+
+
+def test_decode_edge_cases(oracle):
+    """Empty and length-1 sequences, an inactive state, exact ties (first state wins)."""
+    m = random_model(oracle, 4, [2], [], 41)
+    m.pi[:] = 0.25
+    m.B[0, :, :] = 0.5
+    m.A[:] = 0.25
+    m.active[3] = 0
+    off = np.array([0, 0, 1, 6])
+    data = oracle.Data(off, np.zeros((1, 6), np.uint8), np.zeros((0, 6)), None)
+    opath, oscore, otie = oracle.decode(m, data, oracle.DECODE_REFERENCE)
+    with ctx_for(nat, m) as ctx:
+        upload(ctx, data, labels=False)
+        path, score, tie = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+    np.testing.assert_array_equal(path, opath)
+    np.testing.assert_array_equal(tie, otie)
+    assert score[0] == 0.0 and score[1] == 0.0 and (path == 0).all() and (tie & 1).all()
+    np.testing.assert_allclose(score, oscore)
+
+
+# ---------------------------------------------------------------------------------
+# K2-K4 Baum-Welch
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,V,K,lengths", [
+    (10, [10] * 5, [3, 1, 4, 2, 3], [200] * 24),            # config-1 shape
+    (12, [4], [], [200] * 16),                              # toy-robot shape (discrete only)
+    (10, [], [3] * 5, [200] * 16),                          # config-3 shape
+    (64, [10] * 4, [8] * 4, [100] * 6),                     # config-4 states / mixtures (fewer variables)
+    (5, [3], [2], [1, 2, 3, 50, 7, 1]),                     # ragged, incl. length-1 sequences
+])
+def test_estep_statistics_match_oracle(oracle, N, V, K, lengths):
+    m = random_model(oracle, N, V, K, 51)
+    data = sample(oracle, m, lengths, 52)
+    q = perturb(oracle, m, 53)
+    want = oracle.estep(q, data)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        assert got.size == want.size == oracle.stats_size(q)
+        g = ctx.em_posteriors()
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    scale = float(data.P)
+    for key in ("pi", "xi", "gamma", "cat"):
+        np.testing.assert_allclose(sg[key], sw[key], rtol=TOL, atol=TOL * scale / max(1, sw[key].size) + 1e-6, err_msg=key)
+    np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=TOL, atol=1e-3, err_msg="gmm s0")
+    np.testing.assert_allclose(sg["gmm"][..., 1], sw["gmm"][..., 1], rtol=1e-4, atol=2e-3 * np.sqrt(scale), err_msg="gmm s1")
+    np.testing.assert_allclose(sg["gmm"][..., 2], sw["gmm"][..., 2], rtol=1e-4, atol=1e-2 * np.sqrt(scale), err_msg="gmm s2")
+    np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
+
+
+@pytest.mark.parametrize("N,V,K,S,T", [(10, [10] * 5, [3, 1, 4, 2, 3], 64, 200), (12, [4], [], 48, 200), (10, [], [3] * 5, 64, 200)])
+def test_em_iterations_match_oracle(oracle, N, V, K, S, T):
+    """Learned pi / A / categorical / GMM parameters and the per-iteration log-likelihood within
+    1e-5 relative of the fp64 oracle from identical initial parameters (north_star)."""
+    m = random_model(oracle, N, V, K, 61, unit_var=False)
+    data = sample(oracle, m, [T] * S, 62)
+    q = perturb(oracle, m, 63)
+    want = q.copy()
+    ll_want = oracle.em_iterate(want, data, 4)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        ll = ctx.em_iterate(4)
+        np.testing.assert_allclose(ll, ll_want, rtol=TOL)
+        assert (np.diff(ll) > -1e-6 * abs(ll[0])).all()
+        _assert_params(ctx, want, rtol=2e-4, atol=2e-5)
+        p = ctx.get_params()
+    # parameters that carry real mass agree to 1e-5 relative
+    big = want.A > 1e-2
+    np.testing.assert_allclose(p["A"][big], want.A[big], rtol=TOL * 3)
+    np.testing.assert_allclose(p["pi"], want.pi, rtol=TOL * 3, atol=1e-7)
+
+
+def test_bridge_clamped_em_reproduces_supervised_learner(oracle):
+    """One clamped EM iteration == the reference's supervised result: ties the
+    Baum-Welch kernels, which have no reference counterpart, to DNBC.scala:124-220."""
+    ds, learn, _ = _fixture(oracle, "robot_no_momentum_bivariate")
+    sub = oracle.Data.of(ds.learn.select(range(40)))
+    sup = oracle.mle(sub, ds.N, ds.V, None, flags=0)
+    init = sup.copy()
+    rng = np.random.default_rng(71)
+    init.A[:] = rng.random(init.A.shape) + 0.1
+    init.A /= init.A.sum(1, keepdims=True)
+    init.pi[:] = 1.0 / ds.N
+    init.B[:] = 1.0 / ds.V[0]
+    init.mu += 1.0
+    init.var *= 1.5
+    with ctx_for(nat, init) as ctx:
+        upload(ctx, sub, dtype=np.float32)
+        ctx.em_estep(clamp_labels=True)
+        st = oracle.split_stats(init, ctx.em_get_stats())
+        cnt_pi, cnt_A, cnt_B = oracle.mle_counts(ds.N, init.Vmax, sub, 0)
+        np.testing.assert_allclose(st["pi"], cnt_pi, rtol=1e-6, atol=1e-4)
+        np.testing.assert_allclose(st["xi"], cnt_A, rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(st["cat"], cnt_B, rtol=1e-5, atol=1e-3)
+        ctx.em_mstep(sub.S)
+        p = ctx.get_params()
+    np.testing.assert_allclose(p["pi"], sup.pi, atol=1e-6)
+    np.testing.assert_allclose(p["A"], sup.A, atol=1e-5)
+    np.testing.assert_allclose(p["B"], sup.B, atol=1e-5)
+    np.testing.assert_allclose(p["mu"], sup.mu, rtol=1e-5)     # k = 1: closed form mean / variance
+    np.testing.assert_allclose(p["var"], sup.var, rtol=1e-4)
+
+
+def test_large_state_space_kernels(oracle):
+    """N = 300 (padded to 512) exercises the CTA-per-sequence recursions."""
+    m = random_model(oracle, 300, [6], [2], 81, transitions_per_state=40)
+    data = sample(oracle, m, [30, 12, 1, 25], 82)
+    q = perturb(oracle, m, 83)
+    want = oracle.estep(q, data)
+    opath, oscore, otie = oracle.decode(q, data, oracle.DECODE_BACKTRACE)
+    rpath, rscore, rtie = oracle.decode(q, data, oracle.DECODE_REFERENCE)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        path, score, tie = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F64)
+        rp, rs, rt = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    np.testing.assert_allclose(sg["xi"], sw["xi"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(sg["gamma"], sw["gamma"], rtol=1e-4, atol=1e-4)
+    _paths_equal_except_ties(path, opath, tie, otie, data.off)
+    np.testing.assert_allclose(score, oscore, rtol=1e-12)
+    _paths_equal_except_ties(rp, rpath, rt, rtie, data.off)
+
+
+# ---------------------------------------------------------------------------------
+# generator, API surface, host mirror
+# ---------------------------------------------------------------------------------
+def test_device_generator_follows_the_model(oracle):
+    m = random_model(oracle, 6, [5, 3], [2, 1], 91, transitions_per_state=3)
+    with ctx_for(nat, m) as ctx:
+        ctx.generate(400, 50, 1234)
+        off, disc, cont, labels = ctx.download()
+        ctx.generate(400, 50, 1234)
+        off2, disc2, cont2, labels2 = ctx.download(10, 5)
+        cnt_pi, cnt_A, cnt_B = ctx.supervised_counts(0)
+    assert off[-1] == 20000 and (np.diff(off) == 50).all()
+    np.testing.assert_array_equal(labels2, labels[500:750])          # reproducible per (seed, sequence)
+    np.testing.assert_array_equal(cont2, cont[:, 500:750])
+    assert ((cnt_A > 0) <= (m.A > 0)).all()                           # only modelled transitions occur
+    emp = cnt_A / np.maximum(cnt_A.sum(1, keepdims=True), 1)
+    assert np.abs(emp - m.A).max() < 0.05
+    empB = cnt_B / np.maximum(cnt_B.sum(-1, keepdims=True), 1)
+    assert np.abs(empB - m.B).max() < 0.06
+    j = int(np.argmax(np.bincount(labels)))
+    x = cont[1, labels == j]
+    assert abs(x.mean() - m.mu[1, j, 0]) < 0.3 and abs(x.var() - m.var[1, j, 0]) < 0.8
+
+
+def test_error_conventions():
+    with pytest.raises(nat.DnbcError, match="at least one"):
+        nat.Context(3, [2], [0])
+    with nat.Context(3, [2], [1]) as ctx:
+        with pytest.raises(nat.DnbcError, match="needs labels"):
+            ctx.upload([0, 2], np.zeros((1, 2), np.uint8), np.zeros((1, 2)), None)
+            ctx.supervised_counts(0)
+        assert ctx.launch_count() >= 0 and ctx.stream() != 0
+
+
+def test_reference_test_suite_through_the_host_mirror(oracle):
+    """DynamicNaiveBayesianClassifierTest.scala:36-53 and :55-79 against the drop-in API."""
+    from dnbc_scala_b200 import DynamicNaiveBayesianClassifier as DNBC, ObservedState, State
+    valid = ObservedState(["b"], [1.1])
+    invalid = ObservedState(["b", "c"], [1.1])
+    first = State("A", ObservedState(["r"], [42.666]))
+    model = DNBC.mle([[first, State("B", valid)]])
+    with pytest.raises(Exception, match="Number of observed variables is inconsistent"):
+        model.inferMostLikelyHiddenStates([valid, invalid])
+    out = model.inferMostLikelyHiddenStates([valid, valid])
+    assert out == ["A", "A"]          # B has no outgoing transition, so the state set is {A} (DNBC.scala:51)
+    # Scoring: a model learned from generated data scores real observations above shuffled / random ones
+    m = random_model(oracle, 10, [10], [1], 101, transitions_per_state=2)
+    data = sample(oracle, m, [200] * 100, 102)
+    names = [f"h{i}" for i in range(10)]
+    seqs = [[State(names[data.labels[n]], ObservedState([str(data.disc[0, n])], [data.cont[0, n]]))
+             for n in range(data.off[s], data.off[s + 1])] for s in range(data.S)]
+    dnbc = DNBC.mle(iter(seqs))
+    real = [s.ObservedState for s in seqs[0]]
+    rng = np.random.default_rng(103)
+    fake = [ObservedState(real[i].DiscreteVariables, [rng.random() * 30]) for i in rng.permutation(len(real))]
+    score_real, score_fake = dnbc.score(real), dnbc.score(fake)
+    assert score_real * 1.5 > score_fake
+    # and the learned maps equal the oracle's supervised learner under the same state order
+    order = dnbc.states
+    assert sorted(order) == sorted(set(names[j] for j in data.labels))
+    T = dnbc.transitions
+    cnt_pi, cnt_A, _ = oracle.mle_counts(10, 10, data, oracle.QUIRK_TRANSITIONS)
+    for a in T:
+        for b, p in T[a].items():
+            i, j = names.index(a), names.index(b)
+            assert abs(p - cnt_A[i, j] / cnt_A[i].sum()) < 1e-12
