@@ -26,7 +26,7 @@ FAMILIES = ("emission", "forward", "backward", "xi", "stats_gmm", "stats_cat", "
 # every symbol include/dnbc_b200.h declares (tests check the library exports all of them)
 SYMBOLS = (
     "dnbc_abi_version", "dnbc_create", "dnbc_destroy", "dnbc_last_error", "dnbc_set_params",
-    "dnbc_get_params", "dnbc_upload", "dnbc_generate", "dnbc_download", "dnbc_data_shape",
+    "dnbc_get_params", "dnbc_upload", "dnbc_generate", "dnbc_download", "dnbc_download_f32", "dnbc_data_shape",
     "dnbc_emission_logprob", "dnbc_supervised_counts", "dnbc_mle", "dnbc_stats_size",
     "dnbc_em_estep", "dnbc_em_stats_device_ptr", "dnbc_em_get_stats", "dnbc_em_set_stats",
     "dnbc_em_mstep", "dnbc_em_iterate", "dnbc_em_get_posteriors", "dnbc_decode",
@@ -79,6 +79,7 @@ def lib():
         L.dnbc_upload.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.dnbc_generate.argtypes = [vp, i64, C.c_int32, C.c_uint64]
         L.dnbc_download.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+        L.dnbc_download_f32.argtypes = [vp, i64, i64, vp, vp]
         L.dnbc_data_shape.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
         L.dnbc_emission_logprob.argtypes = [vp, i32, vp]
         L.dnbc_supervised_counts.argtypes = [vp, i32, vp, vp, vp]
@@ -112,6 +113,7 @@ class Context:
 
     def __init__(self, n_states: int, alphabet: Sequence[int], mixture: Sequence[int], device: int = 0):
         self._h = None
+        self.device = int(device)
         self.N = int(n_states)
         self.V = np.ascontiguousarray(alphabet, np.int32).reshape(-1)
         self.K = np.ascontiguousarray(mixture, np.int32).reshape(-1)
@@ -195,6 +197,16 @@ class Context:
         lab = np.zeros(P, np.int32) if labels else None
         self._check(lib().dnbc_download(self._h, first, count, _p(off), _p(disc), _p(cont), _p(lab)))
         return off, disc, cont, lab
+
+    def upload_raw(self, n_seq: int, offsets: np.ndarray, disc_ptr: int, cont32_ptr: int, labels_ptr: int = 0):
+        """Upload from caller-owned (e.g. pinned) host buffers given as raw addresses."""
+        off = np.ascontiguousarray(offsets, np.int64)
+        self._check(lib().dnbc_upload(self._h, int(n_seq), _p(off), disc_ptr or None, None, cont32_ptr or None,
+                                      labels_ptr or None))
+        self.S, self.P = int(n_seq), int(off[-1])
+
+    def download_f32_raw(self, first: int, count: int, disc_ptr: int, cont32_ptr: int):
+        self._check(lib().dnbc_download_f32(self._h, first, count, disc_ptr or None, cont32_ptr or None))
 
     # -- kernels ------------------------------------------------------------------
     def emission_logprob(self, precision: int = PREC_F32) -> np.ndarray:

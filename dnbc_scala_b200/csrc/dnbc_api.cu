@@ -164,6 +164,7 @@ extern "C" int dnbc_destroy(dnbc_ctx *c) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -383,6 +384,21 @@ extern "C" int dnbc_download(dnbc_ctx *c, int64_t first, int64_t count, int64_t 
     CU_TRY(c, cudaMemcpyAsync(labels, c->d_labels + p0, (size_t)np * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   }
   CU_TRY(c, cudaStreamSynchronize(st));
+  return DNBC_OK;
+}
+
+extern "C" int dnbc_download_f32(dnbc_ctx *c, int64_t first, int64_t count, uint8_t *disc, float *cont_f32) {
+  if (!c) return DNBC_EINVAL;
+  if (first < 0 || count < 0 || first + count > c->S) return dnbc_fail(c, DNBC_EINVAL, "download: range outside the data");
+  const Dims &d = c->dm;
+  CU_TRY(c, cudaSetDevice(c->device));
+  const int64_t p0 = c->h_off[first], np = c->h_off[first + count] - p0;
+  for (int v = 0; v < d.D && np > 0 && disc; ++v)
+    CU_TRY(c, cudaMemcpyAsync(disc + (size_t)v * np, c->d_disc + (size_t)v * c->P + p0, (size_t)np, cudaMemcpyDeviceToHost, c->stream));
+  for (int v = 0; v < d.C && np > 0 && cont_f32; ++v)
+    CU_TRY(c, cudaMemcpyAsync(cont_f32 + (size_t)v * np, c->d_cont + (size_t)v * c->P + p0, (size_t)np * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
   return DNBC_OK;
 }
 
@@ -712,6 +728,15 @@ extern "C" int dnbc_profile_enable(dnbc_ctx *c, int on) {
 
 extern "C" int dnbc_profile_read(dnbc_ctx *c, double *ms_out, int64_t *launches_out, int reset) {
   if (!c) return DNBC_EINVAL;
+  if (c->ev_used) {
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (size_t q = 0; q < c->ev_used; ++q) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->ev_pool[q].a, c->ev_pool[q].b) == cudaSuccess) c->fam_ms[c->ev_pool[q].fam] += ms;
+    }
+    c->ev_used = 0;
+  }
   for (int f = 0; f < FAM_COUNT; ++f) {
     if (ms_out) ms_out[f] = c->fam_ms[f];
     if (launches_out) launches_out[f] = c->fam_launches[f];

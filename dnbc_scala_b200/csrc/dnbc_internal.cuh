@@ -104,10 +104,15 @@ struct dnbc_ctx {
   int32_t *d_edge_i = nullptr;           // per-edge int workspace
 
   // profiling
+  // (event pairs are only recorded, never waited on, while the stream runs; they are
+  // resolved in dnbc_profile_read so the timed region is not perturbed)
   bool profile = false;
   double fam_ms[FAM_COUNT] = {0};
   int64_t fam_launches[FAM_COUNT] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  struct EvPair { cudaEvent_t a, b; int fam; };
+  std::vector<EvPair> ev_pool;
+  size_t ev_used = 0;
 
   DeviceTables tables() const {
     return DeviceTables{t_pi, t_A, t_At, t_logpi, t_logA, t_cat, t_gs, t_gm, t_gc, d_K, d_active};
@@ -176,18 +181,25 @@ int dnbc_fail(dnbc_ctx *c, int code, const char *fmt, ...);
 struct FamTimer {
   dnbc_ctx *c;
   int fam;
+  dnbc_ctx::EvPair *ev = nullptr;
   FamTimer(dnbc_ctx *ctx, int f) : c(ctx), fam(f) {
     c->launches++;
     c->fam_launches[fam]++;
-    if (c->profile) cudaEventRecord(c->ev0, c->stream);
+    if (c->profile) {
+      if (c->ev_used == c->ev_pool.size()) {
+        dnbc_ctx::EvPair p{nullptr, nullptr, 0};
+        cudaEventCreate(&p.a);
+        cudaEventCreate(&p.b);
+        c->ev_pool.push_back(p);
+      }
+      c->ev_pool[c->ev_used].fam = fam;
+      cudaEventRecord(c->ev_pool[c->ev_used].a, c->stream);
+    }
   }
   ~FamTimer() {
     if (c->profile) {
-      cudaEventRecord(c->ev1, c->stream);
-      cudaEventSynchronize(c->ev1);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-      c->fam_ms[fam] += ms;
+      cudaEventRecord(c->ev_pool[c->ev_used].b, c->stream);
+      c->ev_used++;
     }
   }
 };

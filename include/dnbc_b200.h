@@ -102,6 +102,8 @@ int dnbc_generate(dnbc_ctx *ctx, int64_t n_seq, int32_t seq_len, uint64_t seed);
 /* copies sequences [first, first+count) back (any pointer may be NULL). */
 int dnbc_download(dnbc_ctx *ctx, int64_t first, int64_t count, int64_t *offsets, uint8_t *disc,
                   double *cont_f64, int32_t *labels);
+/* the fp32 observation planes as resident on the device: disc u8 [D][np], cont f32 [C][np] */
+int dnbc_download_f32(dnbc_ctx *ctx, int64_t first, int64_t count, uint8_t *disc, float *cont_f32);
 int dnbc_data_shape(const dnbc_ctx *ctx, int64_t *n_seq, int64_t *n_points);
 
 /* ---- emission log-probabilities (K1): emissionsSum of ...scala:52-56, 79-83 ---- */
