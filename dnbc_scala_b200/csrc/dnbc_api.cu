@@ -556,8 +556,12 @@ extern "C" int dnbc_em_estep(dnbc_ctx *c, int clamp_labels) {
     launch_forward(c, ch.s0, ch.s1, ch.p0);
     launch_backward(c, ch.s0, ch.s1, ch.p0);
     launch_xi(c, ch.np);
-    launch_stats_gmm(c, ch.p0, ch.np);
-    launch_stats_cat(c, ch.p0, ch.np);
+    if (mixture_stats_fast(c)) {
+      launch_mixture_stats(c, ch.p0, ch.np);
+    } else {
+      launch_stats_gmm(c, ch.p0, ch.np);
+      launch_stats_cat(c, ch.p0, ch.np);
+    }
   }
   CU_TRY(c, cudaGetLastError());
   return DNBC_OK;

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) k_emission_f32(Dims dm, DeviceTables tb, 
 
 void launch_emission_f32(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   if (np <= 0) return;
+  if (mixture_emission_fast(c)) return launch_mixture_emission(c, p0, np, out);   // k_mixture.cu
   FamTimer ft(c, FAM_EMISSION);
   constexpr int PPT = 4;
   const int NS = c->dm.Npad < 256 ? c->dm.Npad : 256;

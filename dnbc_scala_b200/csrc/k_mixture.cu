@@ -1,0 +1,433 @@
+// k_mixture.cu -- the two Gaussian-mixture sweeps of an EM iteration.
+//
+//   k_emission_pk (K1): E[p][j] = ln P(o_p | state j)
+//       reference arithmetic: emissionsSum of viterbiInitialize / viterbiCompute,
+//       core/src/main/scala/DynamicNaiveBayesianClassifier.scala:52-56, 79-83;
+//       LearnedDiscreteEdge.probability Edge.scala:69-75; LearnedContinuousEdge.probability
+//       Edge.scala:114-118 -> gaussianMixturePdf GaussianUtils.scala:43-45.
+//   k_stats_pk (K3): fp64 sufficient statistics from the posteriors gamma[p][j]:
+//       GMM responsibilities / moments (generalises EM1D.run's E- and M-step sums,
+//       core/src/main/java/Tools/ExpectationMaximization1D.java:92-124), categorical
+//       histograms (generalises DiscreteEdge.learn, Edge.scala:46-51) and the gamma sums.
+//
+// Both sweeps evaluate every (continuous variable c, state j, component k) Gaussian at every
+// point: ~8.2k exponentials per point at the scale-out shape against 80 B of observations, so
+// they are bound by the MUFU pipe (measured 16 ex2/clk/SM, tools/pipe_peaks.cu) and by
+// instruction issue, not by HBM.  Design rules that follow from the measurements:
+//   * fp32 work is issued as PACKED f32x2 instructions (FFMA2 / FMUL2 / FADD2, two mixture
+//     components per instruction): the FP32 pipe rate is unchanged but the issue slots per
+//     component halve, which is what lets MUFU run near its peak (tools/pipe_peaks2.cu: a body
+//     of 1 MUFU + 8 fp32 ops reaches 96 % of MUFU peak packed, 79 % scalar);
+//   * lanes run over hidden states (32 per warp; several points per warp when N <= 16), so
+//     parameter fetches are conflict-free and E / gamma rows are read and written as whole
+//     128-byte lines;
+//   * emission: every warp evaluates all variables for its own 4 points; coefficients stream
+//     from shared memory (one LDS.128 + one LDS.64 per component pair, amortised over the 4
+//     points); no barriers, no cross-warp traffic, high occupancy;
+//   * statistics: one warp per variable keeps that variable's coefficients AND its 3K moment
+//     accumulators in registers (fp32 over a window of <= 4096 points, in the standardised
+//     variable z and re-centred on the fp64 old mean when flushed: no x^2 - mu^2 cancellation);
+//     categorical bins live in warp-private shared-memory columns (no atomics); each window
+//     ends with one fp64 atomicAdd per statistic.
+#include "dnbc_internal.cuh"
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpk(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 ex2_2(u64 a) {
+  float lo, hi;
+  unpk(a, lo, hi);
+  return pk(ex2_approx(lo), ex2_approx(hi));
+}
+__device__ __forceinline__ float max3lohi(float m, u64 a) {
+  float lo, hi;
+  unpk(a, lo, hi);
+  return fmaxf(m, fmaxf(lo, hi));
+}
+__device__ __forceinline__ float hsum(u64 a) {
+  float lo, hi;
+  unpk(a, lo, hi);
+  return lo + hi;
+}
+
+// ---------------------------------------------------------------------------------
+// K1 emission
+// ---------------------------------------------------------------------------------
+struct EmitArgs {
+  Dims dm;
+  DeviceTables tb;
+  DataView dv;
+  int64_t p0, np;
+  float *E;
+  int LG;       // lanes per point = min(32, Npad)
+  int KP;       // component pairs = ceil(Kmax / 2)
+};
+
+constexpr int EPU = 4;   // points per thread and coefficient fetch
+
+// shared-memory coefficient block of one 32-state slice: [C][KP][32] x {s.lo,s.hi,m.lo,m.hi} then
+// [C][KP][32] x {cc.lo,cc.hi}, then the categorical table [D][Vmax+1][32]
+__global__ void __launch_bounds__(256) k_emission_pk(EmitArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
+  const int LG = a.LG, PG = 32 / LG, KP = a.KP;
+  float4 *sm_sm = (float4 *)smraw;                         // [C*KP*32]
+  float2 *sm_cc = (float2 *)(sm_sm + (size_t)C * KP * 32);  // [C*KP*32]
+  float *sm_cat = (float *)(sm_cc + (size_t)C * KP * 32);   // [D*(Vmax+1)*32]
+  const int lane = threadIdx.x & 31, lj = lane % LG, lp = lane / LG;
+  const int jbase = blockIdx.y * 32;
+  // stage this slice's coefficients (column index = lane slot; slots of the same state repeat)
+  for (int t = threadIdx.x; t < C * KP * 32; t += blockDim.x) {
+    const int sl = t & 31, kp = (t >> 5) % KP, c = (t >> 5) / KP;
+    const int j = jbase + sl % LG;
+    float v[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * kp + h;
+      const bool on = j < N && k < a.tb.K[c];
+      const int64_t o = ((int64_t)c * Kmax + (k < Kmax ? k : 0)) * Npad + (j < Npad ? j : 0);
+      v[h] = on ? a.tb.gs[o] : 0.f;
+      v[2 + h] = on ? a.tb.gm[o] : 0.f;
+      v[4 + h] = on ? a.tb.gc[o] : -INFINITY;
+    }
+    sm_sm[t] = make_float4(v[0], v[1], v[2], v[3]);
+    sm_cc[t] = make_float2(v[4], v[5]);
+  }
+  for (int t = threadIdx.x; t < D * (Vmax + 1) * 32; t += blockDim.x) {
+    const int sl = t & 31, v = (t >> 5) % (Vmax + 1), d = (t >> 5) / (Vmax + 1);
+    const int j = jbase + sl % LG;
+    sm_cat[t] = j < N ? a.tb.cat[((int64_t)d * (Vmax + 1) + v) * Npad + j] : -INFINITY;
+  }
+  __syncthreads();
+  const int j = jbase + lj;
+  const u64 neg1 = pk(-1.f, -1.f);
+  const int64_t group = (int64_t)EPU * PG;                 // points per warp iteration
+  const int64_t ngroups = (a.np + group - 1) / group;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t g = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); g < ngroups; g += (int64_t)gridDim.x * wpb) {
+    int64_t p[EPU];
+    float acc[EPU];
+#pragma unroll
+    for (int i = 0; i < EPU; ++i) {
+      p[i] = g * group + i * PG + lp;
+      acc[i] = 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float *xcol = a.dv.cont + (int64_t)c * a.dv.P + a.p0;
+      u64 xx[EPU], sum2[EPU];
+      float mx[EPU];
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) {
+        const float x = p[i] < a.np ? __ldg(xcol + p[i]) : 0.f;
+        xx[i] = pk(x, x);
+        sum2[i] = 0ull;
+        mx[i] = -INFINITY;
+      }
+      const float4 *ps = sm_sm + (size_t)c * KP * 32 + lane;
+      const float2 *pc = sm_cc + (size_t)c * KP * 32 + lane;
+#pragma unroll 2
+      for (int kp = 0; kp < KP; ++kp) {
+        const float4 sm4 = ps[kp * 32];
+        const float2 cc = pc[kp * 32];
+        const u64 s2 = pk(sm4.x, sm4.y), m2 = pk(sm4.z, sm4.w), cc2 = pk(cc.x, cc.y);
+#pragma unroll
+        for (int i = 0; i < EPU; ++i) {
+          const u64 z2 = fma2(xx[i], s2, m2);
+          const u64 a2 = fma2(mul2(z2, z2), neg1, cc2);
+          mx[i] = max3lohi(mx[i], a2);
+          sum2[i] = add2(sum2[i], ex2_2(a2));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) {
+        float sum = hsum(sum2[i]);
+        float L;
+        if (sum < 1e-30f && mx[i] != -INFINITY) {
+          // every component underflowed fp32 (> ~13 sigma away): redo shifted by the largest
+          // exponent, so the result stays finite where the reference's fp64 sum is finite
+          u64 s = 0ull;
+          const u64 nm = pk(-mx[i], -mx[i]);
+          for (int kp = 0; kp < KP; ++kp) {
+            const float4 sm4 = ps[kp * 32];
+            const float2 cc = pc[kp * 32];
+            const u64 z2 = fma2(xx[i], pk(sm4.x, sm4.y), pk(sm4.z, sm4.w));
+            const u64 a2 = fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y));
+            s = add2(s, ex2_2(add2(a2, nm)));
+          }
+          L = mx[i] + lg2_approx(hsum(s));
+        } else {
+          L = lg2_approx(sum);                       // lg2(0) = -inf: no component has mass
+        }
+        acc[i] += L;
+      }
+    }
+    for (int d = 0; d < D; ++d) {
+      const uint8_t *col = a.dv.disc + (int64_t)d * a.dv.P + a.p0;
+      const float *tab = sm_cat + (size_t)d * (Vmax + 1) * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) {
+        int v = p[i] < a.np ? (int)__ldg(col + p[i]) : Vmax;
+        v = v < Vmax ? v : Vmax;
+        acc[i] += tab[v * 32];
+      }
+    }
+    if (j < N) {
+#pragma unroll
+      for (int i = 0; i < EPU; ++i)
+        if (p[i] < a.np) a.E[p[i] * N + j] = acc[i] * (float)DNBC_LN2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K3 statistics
+// ---------------------------------------------------------------------------------
+struct StatArgs {
+  Dims dm;
+  DeviceTables tb;
+  DataView dv;
+  int64_t p0, np;
+  const float *GA;
+  const double *mu_old;
+  double *gmm, *cat, *gsum;
+  int LG, NW, window;
+};
+
+constexpr int SPB = 8;   // points whose posteriors are fetched together (memory-level parallelism)
+
+template <int KP>
+__global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
+  extern __shared__ float bins[];                           // [warps of this CTA][Vmax+1][32]
+  const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
+  const int LG = a.LG, PG = 32 / LG, NW = a.NW;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, lj = lane % LG, lp = lane / LG;
+  const int j = blockIdx.y * 32 + lj;
+  const int u = blockIdx.z * NW + w;                        // this warp's variable index
+  const bool has_c = u < C, has_d = u < D, jon = j < N;
+  const int bin_d = (Vmax + 1) * 32;
+  float *bd = bins + (size_t)w * bin_d;
+  for (int t = lane; t < bin_d; t += 32) bd[t] = 0.f;
+
+  u64 s2[KP], m2[KP], cc2[KP], S0[KP], S1[KP], S2[KP];
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    float v[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * kp + h;
+      const bool on = has_c && jon && k < a.tb.K[has_c ? u : 0];
+      const int64_t o = ((int64_t)(has_c ? u : 0) * Kmax + (k < Kmax ? k : 0)) * Npad + (j < Npad ? j : 0);
+      v[h] = on ? a.tb.gs[o] : 0.f;
+      v[2 + h] = on ? a.tb.gm[o] : 0.f;
+      v[4 + h] = on ? a.tb.gc[o] : -INFINITY;
+    }
+    s2[kp] = pk(v[0], v[1]); m2[kp] = pk(v[2], v[3]); cc2[kp] = pk(v[4], v[5]);
+    S0[kp] = S1[kp] = S2[kp] = 0ull;
+  }
+  float gs = 0.f;
+  const u64 neg1 = pk(-1.f, -1.f);
+  // contiguous slab of points per CTA column, aligned to 32 so x / symbol loads stay coalesced
+  const int64_t per = ((a.np + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
+  const int64_t pb = (int64_t)blockIdx.x * per;
+  const int64_t pe = pb + per < a.np ? pb + per : a.np;
+  const float *xcol = a.dv.cont + (int64_t)(has_c ? u : 0) * a.dv.P + a.p0;
+  const uint8_t *dcol = a.dv.disc + (int64_t)(has_d ? u : 0) * a.dv.P + a.p0;
+  const float *gcol = a.GA + (jon ? j : 0);
+  int inwin = 0;
+  for (int64_t base = pb; base < pe; base += 32) {
+    float xreg = 0.f;
+    int vreg = Vmax;
+    if (base + lane < pe) {
+      if (has_c) xreg = __ldg(xcol + base + lane);
+      if (has_d) vreg = (int)__ldg(dcol + base + lane);
+    }
+    vreg = vreg < Vmax ? vreg : Vmax;
+    for (int blk = 0; blk < LG; blk += SPB) {              // LG steps of PG points cover the 32 points
+      float g[SPB];
+#pragma unroll
+      for (int i = 0; i < SPB; ++i) {
+        const int64_t p = base + (blk + i) * PG + lp;
+        g[i] = (blk + i < LG && p < pe && jon) ? __ldg(gcol + p * N) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < SPB; ++i) {
+        if (blk + i >= LG) break;
+        const int qp = (blk + i) * PG + lp;
+        if (has_c) {
+          const float x = __shfl_sync(0xffffffffu, xreg, qp);
+          const u64 xx = pk(x, x);
+          u64 e2[KP], z2[KP], zz2[KP], sum2 = 0ull;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            z2[kp] = fma2(xx, s2[kp], m2[kp]);
+            zz2[kp] = mul2(z2[kp], z2[kp]);
+            const u64 a2 = fma2(zz2[kp], neg1, cc2[kp]);
+            mx = max3lohi(mx, a2);
+            e2[kp] = ex2_2(a2);
+            sum2 = add2(sum2, e2[kp]);
+          }
+          float sum = hsum(sum2);
+          if (sum < 1e-30f && mx != -INFINITY) {           // all components underflowed: redo shifted
+            const u64 nm = pk(-mx, -mx);
+            sum2 = 0ull;
+#pragma unroll
+            for (int kp = 0; kp < KP; ++kp) {
+              e2[kp] = ex2_2(add2(fma2(zz2[kp], neg1, cc2[kp]), nm));
+              sum2 = add2(sum2, e2[kp]);
+            }
+            sum = hsum(sum2);
+          }
+          const float inv = sum > 0.f ? g[i] * rcp_approx(sum) : 0.f;
+          const u64 inv2 = pk(inv, inv);
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const u64 rr = mul2(e2[kp], inv2);
+            S0[kp] = add2(S0[kp], rr);
+            S1[kp] = fma2(rr, z2[kp], S1[kp]);
+            S2[kp] = fma2(rr, zz2[kp], S2[kp]);
+          }
+        }
+        if (has_d) {                                       // categorical histogram: bins[v][lane] += gamma
+          const int v = __shfl_sync(0xffffffffu, vreg, qp);
+          bd[v * 32 + lane] += g[i];
+        }
+        if (u == 0) gs += g[i];
+      }
+    }
+    inwin += 32;
+    if (inwin >= a.window || base + 32 >= pe) {
+      inwin = 0;
+      if (has_c && jon) {
+        const int K = a.tb.K[u];
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) {
+          float sv[2], mv[2], a0[2], a1[2], a2v[2];
+          unpk(s2[kp], sv[0], sv[1]); unpk(m2[kp], mv[0], mv[1]);
+          unpk(S0[kp], a0[0], a0[1]); unpk(S1[kp], a1[0], a1[1]); unpk(S2[kp], a2v[0], a2v[1]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = 2 * kp + h;
+            if (k < K && a0[h] != 0.f) {
+              // z = (x - mu') s with mu' = -m/s the fp32-rounded centre; re-centre on the fp64 old mean
+              const int64_t dst = ((int64_t)u * N + j) * Kmax + k;
+              const double s = (double)sv[h];
+              double m0 = (double)a0[h], m1 = 0.0, m2d = 0.0;
+              if (s > 0.0) {
+                const double delta = -(double)mv[h] / s - a.mu_old[dst];
+                const double b1 = (double)a1[h] / s, b2 = (double)a2v[h] / (s * s);
+                m1 = b1 + delta * m0;
+                m2d = b2 + 2.0 * delta * b1 + delta * delta * m0;
+              }
+              atomicAdd(a.gmm + 3 * dst + 0, m0);
+              atomicAdd(a.gmm + 3 * dst + 1, m1);
+              atomicAdd(a.gmm + 3 * dst + 2, m2d);
+            }
+          }
+          S0[kp] = S1[kp] = S2[kp] = 0ull;
+        }
+      }
+      if (u == 0) {
+        if (jon && gs != 0.f) atomicAdd(a.gsum + j, (double)gs);
+        gs = 0.f;
+      }
+      if (has_d) {
+        for (int v = 0; v < Vmax; ++v) {
+          const float b = bd[v * 32 + lane];
+          if (b != 0.f && jon) atomicAdd(a.cat + ((int64_t)u * N + j) * Vmax + v, (double)b);
+          bd[v * 32 + lane] = 0.f;
+        }
+        bd[Vmax * 32 + lane] = 0.f;                        // unseen-symbol row is discarded
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------
+static size_t emit_smem(const Dims &d, int KP) {
+  return (size_t)d.C * KP * 32 * (sizeof(float4) + sizeof(float2)) + (size_t)d.D * (d.Vmax + 1) * 32 * sizeof(float);
+}
+
+bool mixture_emission_fast(const dnbc_ctx *c) {
+  const int KP = (c->dm.Kmax + 1) / 2;
+  return emit_smem(c->dm, KP) <= 100 * 1024;
+}
+// the statistics sweep keeps 3K coefficients + 3K accumulators in registers and handles one
+// continuous and one discrete variable per warp
+bool mixture_stats_fast(const dnbc_ctx *c) {
+  const Dims &d = c->dm;
+  const int units = d.C > d.D ? d.C : d.D;
+  return d.Kmax <= 8 && units <= 64 && (size_t)8 * (d.Vmax + 1) * 32 * sizeof(float) <= 96 * 1024;
+}
+
+void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
+  if (np <= 0) return;
+  FamTimer ft(c, FAM_EMISSION);
+  const Dims &d = c->dm;
+  EmitArgs a{d, c->tables(), c->data(), p0, np, out, d.Npad < 32 ? d.Npad : 32, (d.Kmax + 1) / 2};
+  const size_t smem = emit_smem(d, a.KP);
+  const int gy = (d.Npad + 31) / 32;
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm > 6) per_sm = 6;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t group = (int64_t)EPU * (32 / a.LG);
+  int64_t gx = (int64_t)c->sm_count * per_sm / gy;
+  const int64_t maxgx = ((np + group - 1) / group + 7) / 8;
+  if (gx > maxgx) gx = maxgx;
+  if (gx < 1) gx = 1;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_emission_pk<<<dim3((unsigned)gx, (unsigned)gy), 256, smem, c->stream>>>(a);
+}
+
+// GMM moments + categorical histograms + gamma sums in one sweep over the posteriors
+void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
+  if (np <= 0) return;
+  FamTimer ft(c, FAM_STATS_GMM);
+  const Dims &d = c->dm;
+  StatsLayout sl = stats_layout(d);
+  int units = d.C > d.D ? d.C : d.D;
+  if (units < 1) units = 1;
+  const int NW = units > 8 ? 8 : units;
+  const int gz = (units + NW - 1) / NW, gy = (d.Npad + 31) / 32;
+  StatArgs a{d, c->tables(), c->data(), p0, np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
+             c->d_stats + sl.gamma, d.Npad < 32 ? d.Npad : 32, NW, 4096};
+  const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
+  int64_t gx = (int64_t)c->sm_count * 2 * (8 / NW > 4 ? 4 : 8 / NW) / ((int64_t)gy * gz);
+  const int64_t maxgx = (np + 255) / 256;
+  if (gx > maxgx) gx = maxgx;
+  if (gx < 1) gx = 1;
+  const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
+  const int KP = (d.Kmax + 1) / 2;
+#define STATS_CASE(KP_)                                                                                              \
+  if (KP == KP_) {                                                                                                   \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_stats_pk<KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    k_stats_pk<KP_><<<grid, NW * 32, smem, c->stream>>>(a);                                                          \
+    return;                                                                                                          \
+  }
+  STATS_CASE(1) STATS_CASE(2) STATS_CASE(3) STATS_CASE(4)
+#undef STATS_CASE
+}
