@@ -437,6 +437,7 @@ static int64_t chunk_budget_points(const dnbc_ctx *c, size_t bytes_per_point) {
   size_t held = 0;  // scratch we already own can be reused
   size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)12 << 30);
   int64_t pts = (int64_t)(budget / std::max<size_t>(bytes_per_point, 1));
+  pts = std::min<int64_t>(pts, (int64_t)1 << 30);   // kernels index chunk-relative points with 32 bits
   pts = std::max<int64_t>(pts, c->Tmax);
   return std::min<int64_t>(pts, std::max<int64_t>(c->P, 1));
 }

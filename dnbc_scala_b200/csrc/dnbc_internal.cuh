@@ -157,6 +157,8 @@ bool mixture_emission_fast(const dnbc_ctx *c);
 bool mixture_stats_fast(const dnbc_ctx *c);
 void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out);
 void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np);
+bool fb2_supported(const dnbc_ctx *c);
+void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 void launch_fb_block(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 void launch_decode_block_f32(dnbc_ctx *c, int mode, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path,
                              double *score, uint8_t *tie, void *bp);

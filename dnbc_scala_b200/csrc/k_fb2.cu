@@ -1,0 +1,294 @@
+// k_fb2.cu -- K2: scaled forward / backward recursions with the transition matrix held in
+// REGISTERS (state spaces up to 64).
+//
+// The reference has NO forward-backward: its learner is supervised counting
+// (DynamicNaiveBayesianClassifier.scala:124-161).  These kernels implement SURVEY Appendix B
+// and are checked against the fp64 oracle (oracle/dnbc_oracle.c fb_one) and, through the
+// clamped-label bridge test, against the reference's supervised counts.
+//
+// Mapping: a group of LG = min(32, Npad) lanes owns SQ = 2 sequences at a time (two
+// independent dependency chains per lane); lane l holds states l, l + LG (R per lane).
+//   forward : lane keeps COLUMN j of A (alpha_t(j) = b_t(j) sum_i alpha_{t-1}(i) a_ij)
+//   backward: lane keeps ROW i of A    (beta_t(i) = sum_j a_ij u_t(j))
+// so the N^2 multiply-adds of a step read the matrix from registers; the previous vector is
+// exchanged through a warp-private shared-memory line and read back as broadcast LDS.128
+// (N/4 loads per step instead of the N shuffles + 2N matrix loads of the first version, which
+// ncu showed to be 90 % overhead instructions).  The per-step normaliser is a shuffle
+// reduction inside the group.  Groups are persistent and walk sequences with a grid stride.
+#include "dnbc_internal.cuh"
+
+template <int LG>
+__device__ __forceinline__ unsigned gmask() {
+  if (LG == 32) return 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  return ((1u << (LG & 31)) - 1u) << ((lane / LG) * LG);
+}
+template <int LG>
+__device__ __forceinline__ float gmax(float v, unsigned mask) {
+#pragma unroll
+  for (int o = LG / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, LG));
+  return v;
+}
+template <int LG>
+__device__ __forceinline__ float gsum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = LG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, LG);
+  return v;
+}
+
+struct Fb2Args {
+  Dims dm;
+  DeviceTables tb;
+  const int64_t *off;
+  int64_t s0, s1, p0;
+  const float *E;   // [np][N] natural-log emissions (chunk-relative rows)
+  float *AL;        // [np][N] scaled alpha
+  float *GA;        // [np][N] gamma
+  float *U;         // [np][N] u_t(j) = b~_{t+1}(j) beta_{t+1}(j) / c_{t+1}  (0 on the last step)
+  float *cs;        // [np]    c_t
+  double *stats;    // packed statistics ([0] = log-likelihood)
+  int64_t st_pi;    // offset of the pi-stat
+};
+
+constexpr int FB_WARPS = 4;
+
+// dot products of the shared vector with this lane's R matrix lines (4 partial sums per line)
+template <int NP, int R>
+__device__ __forceinline__ void matvec(const float *vec, const float (&M)[R][NP], float (&out)[R]) {
+  float part[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[r][q] = 0.f;
+  if (NP % 4 == 0) {
+    const float4 *v4 = (const float4 *)vec;
+#pragma unroll
+    for (int i4 = 0; i4 < NP / 4; ++i4) {
+      const float4 v = v4[i4];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        part[r][0] = fmaf(v.x, M[r][4 * i4 + 0], part[r][0]);
+        part[r][1] = fmaf(v.y, M[r][4 * i4 + 1], part[r][1]);
+        part[r][2] = fmaf(v.z, M[r][4 * i4 + 2], part[r][2]);
+        part[r][3] = fmaf(v.w, M[r][4 * i4 + 3], part[r][3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+#pragma unroll
+      for (int r = 0; r < R; ++r) part[r][i & 3] = fmaf(vec[i], M[r][i], part[r][i & 3]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = (part[r][0] + part[r][1]) + (part[r][2] + part[r][3]);
+}
+
+// ---- forward: alpha^_t(j) = b~_t(j) sum_i alpha^_{t-1}(i) a_ij / c_t ;  LL += ln c_t + m_t
+template <int LG, int R, int SQ>
+__global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
+  constexpr int NP = LG * R, PG = 32 / LG;
+  __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
+  const int N = a.dm.N, Npad = a.dm.Npad;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
+  const unsigned mask = gmask<LG>();
+  float Acol[R][NP], pi[R];
+  int jr[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    jr[r] = lj + LG * r;
+    pi[r] = jr[r] < N ? a.tb.pi[jr[r]] : 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) Acol[r][i] = (i < N && jr[r] < N) ? a.tb.A[i * Npad + jr[r]] : 0.f;
+  }
+  const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;
+  const int64_t gid = ((int64_t)blockIdx.x * FB_WARPS + w) * PG + gi;
+  double ll = 0.0;
+  for (int64_t sb = a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
+    int64_t row[SQ], pt[SQ];
+    int T[SQ], Tmax = 0;
+    float alpha[SQ][R], en[SQ][R];
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+      const int64_t s = sb + q;
+      T[q] = s < a.s1 ? (int)(a.off[s + 1] - a.off[s]) : 0;
+      pt[q] = s < a.s1 ? a.off[s] - a.p0 : 0;
+      row[q] = pt[q] * N;
+      Tmax = T[q] > Tmax ? T[q] : Tmax;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        alpha[q][r] = 0.f;
+        en[q][r] = (T[q] > 0 && jr[r] < N) ? a.E[row[q] + jr[r]] : -INFINITY;
+      }
+    }
+    for (int t = 0; t < Tmax; ++t) {
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        const bool live = t < T[q];
+        float e[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          e[r] = en[q][r];
+          en[q][r] = (t + 1 < T[q] && jr[r] < N) ? a.E[row[q] + (int64_t)(t + 1) * N + jr[r]] : -INFINITY;
+        }
+        float m = e[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) m = fmaxf(m, e[r]);
+        m = gmax<LG>(m, mask);
+        if (m == -INFINITY) m = 0.f;
+        float acc[R];
+        if (t == 0) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = pi[r];
+        } else {
+          float *vec = sv[w][gi][q];
+#pragma unroll
+          for (int r = 0; r < R; ++r) vec[jr[r]] = alpha[q][r];
+          __syncwarp(mask);
+          matvec<NP, R>(vec, Acol, acc);
+          __syncwarp(mask);
+        }
+        float csum = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r] *= ex2_approx((e[r] - m) * (float)DNBC_LOG2E);
+          csum += acc[r];
+        }
+        csum = gsum<LG>(csum, mask);
+        const float inv = 1.0f / csum;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          alpha[q][r] = acc[r] * inv;
+          if (live && jr[r] < N) a.AL[row[q] + (int64_t)t * N + jr[r]] = alpha[q][r];
+        }
+        if (live && lj == 0) {
+          a.cs[pt[q] + t] = csum;
+          ll += (double)logf(csum) + (double)m;
+        }
+      }
+    }
+  }
+  if (lj == 0 && ll != 0.0) atomicAdd(a.stats, ll);
+}
+
+// ---- backward: beta^_t(i) = sum_j a_ij u_t(j),  u_t(j) = b~_{t+1}(j) beta^_{t+1}(j) / c_{t+1};
+//      gamma_t = alpha^_t beta^_t;  pi-stat += gamma_0
+template <int LG, int R, int SQ>
+__global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
+  constexpr int NP = LG * R, PG = 32 / LG;
+  __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
+  const int N = a.dm.N, Npad = a.dm.Npad;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
+  const unsigned mask = gmask<LG>();
+  float Arow[R][NP];
+  int ir[R];
+  double piacc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    ir[r] = lj + LG * r;
+    piacc[r] = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < NP; ++jj) Arow[r][jj] = (jj < N && ir[r] < N) ? a.tb.A[ir[r] * Npad + jj] : 0.f;
+  }
+  const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;
+  const int64_t gid = ((int64_t)blockIdx.x * FB_WARPS + w) * PG + gi;
+  for (int64_t sb = a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
+    int64_t row[SQ], pt[SQ];
+    int T[SQ], Tmax = 0;
+    float beta[SQ][R], aln[SQ][R], en[SQ][R], csn[SQ];
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+      const int64_t s = sb + q;
+      T[q] = s < a.s1 ? (int)(a.off[s + 1] - a.off[s]) : 0;
+      pt[q] = s < a.s1 ? a.off[s] - a.p0 : 0;
+      row[q] = pt[q] * N;
+      Tmax = T[q] > Tmax ? T[q] : Tmax;
+      csn[q] = 1.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        beta[q][r] = 1.f;
+        aln[q][r] = (T[q] > 0 && ir[r] < N) ? a.AL[row[q] + (int64_t)(T[q] - 1) * N + ir[r]] : 0.f;
+        en[q][r] = -INFINITY;
+      }
+    }
+    // sequences of a pair are aligned at their LAST step: step index k counts back from it
+    for (int k = 0; k < Tmax; ++k) {
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        const int t = T[q] - 1 - k;
+        const bool live = t >= 0;
+        float al[R], e[R];
+        const float c_next = csn[q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          al[r] = aln[q][r];
+          e[r] = en[q][r];
+          // prefetch for step t-1: alpha_{t-1}, and E_t / c_t (the "t+1" quantities of step t-1)
+          aln[q][r] = (t > 0 && ir[r] < N) ? a.AL[row[q] + (int64_t)(t - 1) * N + ir[r]] : 0.f;
+          en[q][r] = (t > 0 && ir[r] < N) ? a.E[row[q] + (int64_t)t * N + ir[r]] : -INFINITY;
+        }
+        csn[q] = t > 0 ? a.cs[pt[q] + t] : 1.f;
+        if (k > 0) {
+          float m = e[0];
+#pragma unroll
+          for (int r = 1; r < R; ++r) m = fmaxf(m, e[r]);
+          m = gmax<LG>(m, mask);
+          if (m == -INFINITY) m = 0.f;
+          const float ic = 1.0f / c_next;
+          float *vec = sv[w][gi][q];
+          float u[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            u[r] = ex2_approx((e[r] - m) * (float)DNBC_LOG2E) * beta[q][r] * ic;
+            if (live && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = u[r];
+            vec[ir[r]] = u[r];
+          }
+          __syncwarp(mask);
+          matvec<NP, R>(vec, Arow, beta[q]);
+          __syncwarp(mask);
+        } else if (live) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float g = al[r] * beta[q][r];
+          if (live && ir[r] < N) a.GA[row[q] + (int64_t)t * N + ir[r]] = g;
+          if (t == 0) piacc[r] += (double)g;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (ir[r] < N && piacc[r] != 0.0) atomicAdd(a.stats + a.st_pi + ir[r], piacc[r]);
+}
+
+template <int LG, int R>
+static void launch_fb2_t(dnbc_ctx *c, const Fb2Args &a, bool backward) {
+  constexpr int SQ = 2, PG = 32 / LG;
+  const int64_t nseq = a.s1 - a.s0;
+  const int64_t per_block = (int64_t)FB_WARPS * PG * SQ;
+  int64_t blocks = (nseq + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)c->sm_count * (LG * R > 32 ? 2 : 4);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (backward) k_backward2<LG, R, SQ><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
+  else k_forward2<LG, R, SQ><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
+}
+
+bool fb2_supported(const dnbc_ctx *c) { return c->dm.Npad <= 64; }
+
+void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) {
+  StatsLayout sl = stats_layout(c->dm);
+  Fb2Args a{c->dm, c->tables(), c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi};
+  switch (c->dm.Npad) {
+    case 1:
+    case 2: launch_fb2_t<2, 1>(c, a, backward); break;
+    case 4: launch_fb2_t<4, 1>(c, a, backward); break;
+    case 8: launch_fb2_t<8, 1>(c, a, backward); break;
+    case 16: launch_fb2_t<16, 1>(c, a, backward); break;
+    case 32: launch_fb2_t<32, 1>(c, a, backward); break;
+    default: launch_fb2_t<32, 2>(c, a, backward); break;   // Npad == 64
+  }
+}

@@ -250,6 +250,7 @@ static void launch_fb_t(dnbc_ctx *c, const FbArgs &a, bool backward) {
 static void launch_fb(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) {
   if (s1 <= s0) return;
   FamTimer ft(c, backward ? FAM_BACKWARD : FAM_FORWARD);
+  if (fb2_supported(c)) return launch_fb2(c, s0, s1, p0, backward);   // register-resident A (k_fb2.cu)
   StatsLayout sl = stats_layout(c->dm);
   FbArgs a{c->dm, c->tables(), c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi};
   switch (c->dm.Npad) {

@@ -57,9 +57,10 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   return d;
 }
 __device__ __forceinline__ u64 ex2_2(u64 a) {
-  float lo, hi;
-  unpk(a, lo, hi);
-  return pk(ex2_approx(lo), ex2_approx(hi));
+  u64 d;
+  asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tex2.approx.ftz.f32 lo, lo;\n\tex2.approx.ftz.f32 hi, hi;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}" : "=l"(d) : "l"(a));
+  return d;
 }
 __device__ __forceinline__ float max3lohi(float m, u64 a) {
   float lo, hi;
@@ -79,21 +80,71 @@ struct EmitArgs {
   Dims dm;
   DeviceTables tb;
   DataView dv;
-  int64_t p0, np;
+  int64_t p0;
+  int np;       // points of this launch (chunks are capped below 2^30 points)
   float *E;
   int LG;       // lanes per point = min(32, Npad)
-  int KP;       // component pairs = ceil(Kmax / 2)
+  int vec;      // observation planes are 16-byte aligned at every group of 4 points
 };
 
 constexpr int EPU = 4;   // points per thread and coefficient fetch
 
+// one variable, EPU points: log2 mixture density added to acc[]
+template <int KP>
+__device__ __forceinline__ void emit_var(const float4 *ps, const float2 *pc, const float (&x)[EPU], float (&acc)[EPU]) {
+  const u64 neg1 = pk(-1.f, -1.f);
+  u64 xx[EPU], sum2[EPU];
+  float mx[EPU];
+#pragma unroll
+  for (int i = 0; i < EPU; ++i) {
+    xx[i] = pk(x[i], x[i]);
+    sum2[i] = 0ull;
+    mx[i] = -INFINITY;
+  }
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    const float4 sm4 = ps[kp * 32];
+    const float2 cc = pc[kp * 32];
+    const u64 s2 = pk(sm4.x, sm4.y), m2 = pk(sm4.z, sm4.w), cc2 = pk(cc.x, cc.y);
+#pragma unroll
+    for (int i = 0; i < EPU; ++i) {
+      const u64 z2 = fma2(xx[i], s2, m2);
+      const u64 a2 = fma2(mul2(z2, z2), neg1, cc2);
+      mx[i] = max3lohi(mx[i], a2);
+      sum2[i] = add2(sum2[i], ex2_2(a2));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < EPU; ++i) {
+    const float sum = hsum(sum2[i]);
+    float L = lg2_approx(sum);                       // lg2(0) = -inf: no component has mass
+    if (sum < 1e-30f && mx[i] != -INFINITY) {
+      // every component underflowed fp32 (> ~13 sigma away): redo shifted by the largest
+      // exponent, so the result stays finite where the reference's fp64 sum is finite
+      u64 s = 0ull;
+      const u64 nm = pk(-mx[i], -mx[i]);
+#pragma unroll 1
+      for (int kp = 0; kp < KP; ++kp) {
+        const float4 sm4 = ps[kp * 32];
+        const float2 cc = pc[kp * 32];
+        const u64 z2 = fma2(xx[i], pk(sm4.x, sm4.y), pk(sm4.z, sm4.w));
+        const u64 a2 = fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y));
+        s = add2(s, ex2_2(add2(a2, nm)));
+      }
+      L = mx[i] + lg2_approx(hsum(s));
+    }
+    acc[i] += L;
+  }
+}
+
 // shared-memory coefficient block of one 32-state slice: [C][KP][32] x {s.lo,s.hi,m.lo,m.hi} then
 // [C][KP][32] x {cc.lo,cc.hi}, then the categorical table [D][Vmax+1][32]
-__global__ void __launch_bounds__(256) k_emission_pk(EmitArgs a) {
+template <int KP>
+__global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
-  const int LG = a.LG, PG = 32 / LG, KP = a.KP;
-  float4 *sm_sm = (float4 *)smraw;                         // [C*KP*32]
+  const int LG = a.LG, PG = 32 / LG;
+  float4 *sm_sm = (float4 *)smraw;                          // [C*KP*32]
   float2 *sm_cc = (float2 *)(sm_sm + (size_t)C * KP * 32);  // [C*KP*32]
   float *sm_cat = (float *)(sm_cc + (size_t)C * KP * 32);   // [D*(Vmax+1)*32]
   const int lane = threadIdx.x & 31, lj = lane % LG, lp = lane / LG;
@@ -122,81 +173,67 @@ __global__ void __launch_bounds__(256) k_emission_pk(EmitArgs a) {
   }
   __syncthreads();
   const int j = jbase + lj;
-  const u64 neg1 = pk(-1.f, -1.f);
-  const int64_t group = (int64_t)EPU * PG;                 // points per warp iteration
-  const int64_t ngroups = (a.np + group - 1) / group;
+  const int group = EPU * PG;                               // points per warp iteration
+  const int ngroups = (a.np + group - 1) / group;
   const int wpb = blockDim.x >> 5;
-  for (int64_t g = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); g < ngroups; g += (int64_t)gridDim.x * wpb) {
-    int64_t p[EPU];
+  const float *cont0 = a.dv.cont + a.p0;
+  const uint8_t *disc0 = a.dv.disc + a.p0;
+  const int64_t P = a.dv.P;
+  const bool vec = a.vec && PG == 1;
+  const int cstride = KP * 32;
+  for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * wpb) {
+    const int pb = g * group;
+    const bool full = pb + group <= a.np;
+    int po[EPU];                                            // this lane's points (chunk-relative)
+#pragma unroll
+    for (int i = 0; i < EPU; ++i) po[i] = pb + i * PG + lp;
     float acc[EPU];
 #pragma unroll
-    for (int i = 0; i < EPU; ++i) {
-      p[i] = g * group + i * PG + lp;
-      acc[i] = 0.f;
-    }
+    for (int i = 0; i < EPU; ++i) acc[i] = 0.f;
+    // observations of variable c for this lane's EPU points; fetched one variable ahead
+    auto load_x = [&](int c, float (&x)[EPU]) {
+      const float *col = cont0 + (int64_t)c * P;
+      if (vec && full) {
+        const float4 v = __ldg((const float4 *)(col + pb));
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPU; ++i) x[i] = po[i] < a.np ? __ldg(col + po[i]) : 0.f;
+      }
+    };
+    float xc[EPU], xn[EPU];
+    if (C > 0) load_x(0, xc);
+    const float4 *ps = sm_sm + lane;
+    const float2 *pc = sm_cc + lane;
     for (int c = 0; c < C; ++c) {
-      const float *xcol = a.dv.cont + (int64_t)c * a.dv.P + a.p0;
-      u64 xx[EPU], sum2[EPU];
-      float mx[EPU];
+      if (c + 1 < C) load_x(c + 1, xn);
+      emit_var<KP>(ps, pc, xc, acc);
+      ps += cstride;
+      pc += cstride;
 #pragma unroll
-      for (int i = 0; i < EPU; ++i) {
-        const float x = p[i] < a.np ? __ldg(xcol + p[i]) : 0.f;
-        xx[i] = pk(x, x);
-        sum2[i] = 0ull;
-        mx[i] = -INFINITY;
-      }
-      const float4 *ps = sm_sm + (size_t)c * KP * 32 + lane;
-      const float2 *pc = sm_cc + (size_t)c * KP * 32 + lane;
-#pragma unroll 2
-      for (int kp = 0; kp < KP; ++kp) {
-        const float4 sm4 = ps[kp * 32];
-        const float2 cc = pc[kp * 32];
-        const u64 s2 = pk(sm4.x, sm4.y), m2 = pk(sm4.z, sm4.w), cc2 = pk(cc.x, cc.y);
-#pragma unroll
-        for (int i = 0; i < EPU; ++i) {
-          const u64 z2 = fma2(xx[i], s2, m2);
-          const u64 a2 = fma2(mul2(z2, z2), neg1, cc2);
-          mx[i] = max3lohi(mx[i], a2);
-          sum2[i] = add2(sum2[i], ex2_2(a2));
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) {
-        float sum = hsum(sum2[i]);
-        float L;
-        if (sum < 1e-30f && mx[i] != -INFINITY) {
-          // every component underflowed fp32 (> ~13 sigma away): redo shifted by the largest
-          // exponent, so the result stays finite where the reference's fp64 sum is finite
-          u64 s = 0ull;
-          const u64 nm = pk(-mx[i], -mx[i]);
-          for (int kp = 0; kp < KP; ++kp) {
-            const float4 sm4 = ps[kp * 32];
-            const float2 cc = pc[kp * 32];
-            const u64 z2 = fma2(xx[i], pk(sm4.x, sm4.y), pk(sm4.z, sm4.w));
-            const u64 a2 = fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y));
-            s = add2(s, ex2_2(add2(a2, nm)));
-          }
-          L = mx[i] + lg2_approx(hsum(s));
-        } else {
-          L = lg2_approx(sum);                       // lg2(0) = -inf: no component has mass
-        }
-        acc[i] += L;
-      }
+      for (int i = 0; i < EPU; ++i) xc[i] = xn[i];
     }
+    const float *tab = sm_cat + lane;
     for (int d = 0; d < D; ++d) {
-      const uint8_t *col = a.dv.disc + (int64_t)d * a.dv.P + a.p0;
-      const float *tab = sm_cat + (size_t)d * (Vmax + 1) * 32 + lane;
+      const uint8_t *col = disc0 + (int64_t)d * P;
+      int v[EPU];
+      if (vec && full) {
+        const uint32_t w4 = __ldg((const uint32_t *)(col + pb));
 #pragma unroll
-      for (int i = 0; i < EPU; ++i) {
-        int v = p[i] < a.np ? (int)__ldg(col + p[i]) : Vmax;
-        v = v < Vmax ? v : Vmax;
-        acc[i] += tab[v * 32];
+        for (int i = 0; i < EPU; ++i) v[i] = (int)((w4 >> (8 * i)) & 0xffu);
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPU; ++i) v[i] = po[i] < a.np ? (int)__ldg(col + po[i]) : Vmax;
       }
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) acc[i] += tab[(v[i] < Vmax ? v[i] : Vmax) * 32];
+      tab += (Vmax + 1) * 32;
     }
     if (j < N) {
+      float *dst = a.E + (int64_t)pb * N + j;
 #pragma unroll
       for (int i = 0; i < EPU; ++i)
-        if (p[i] < a.np) a.E[p[i] * N + j] = acc[i] * (float)DNBC_LN2;
+        if (full || po[i] < a.np) dst[(int64_t)(i * PG + lp) * N] = acc[i] * (float)DNBC_LN2;
     }
   }
 }
@@ -208,7 +245,8 @@ struct StatArgs {
   Dims dm;
   DeviceTables tb;
   DataView dv;
-  int64_t p0, np;
+  int64_t p0;
+  int np;
   const float *GA;
   const double *mu_old;
   double *gmm, *cat, *gsum;
@@ -216,6 +254,49 @@ struct StatArgs {
 };
 
 constexpr int SPB = 8;   // points whose posteriors are fetched together (memory-level parallelism)
+
+template <int KP>
+struct StatRegs {
+  u64 s2[KP], m2[KP], cc2[KP], S0[KP], S1[KP], S2[KP];
+};
+
+// one point: responsibilities of this warp's variable, weighted by the posterior g
+template <int KP>
+__device__ __forceinline__ void stat_point(StatRegs<KP> &q, float x, float g) {
+  const u64 neg1 = pk(-1.f, -1.f);
+  const u64 xx = pk(x, x);
+  u64 e2[KP], z2[KP], zz2[KP], sum2 = 0ull;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    z2[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
+    zz2[kp] = mul2(z2[kp], z2[kp]);
+    const u64 a2 = fma2(zz2[kp], neg1, q.cc2[kp]);
+    mx = max3lohi(mx, a2);
+    e2[kp] = ex2_2(a2);
+    sum2 = add2(sum2, e2[kp]);
+  }
+  float sum = hsum(sum2);
+  if (sum < 1e-30f && mx != -INFINITY) {                   // all components underflowed: redo shifted
+    const u64 nm = pk(-mx, -mx);
+    sum2 = 0ull;
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp) {
+      e2[kp] = ex2_2(add2(fma2(zz2[kp], neg1, q.cc2[kp]), nm));
+      sum2 = add2(sum2, e2[kp]);
+    }
+    sum = hsum(sum2);
+  }
+  const float inv = sum > 0.f ? g * rcp_approx(sum) : 0.f;
+  const u64 inv2 = pk(inv, inv);
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    const u64 rr = mul2(e2[kp], inv2);
+    q.S0[kp] = add2(q.S0[kp], rr);
+    q.S1[kp] = fma2(rr, z2[kp], q.S1[kp]);
+    q.S2[kp] = fma2(rr, zz2[kp], q.S2[kp]);
+  }
+}
 
 template <int KP>
 __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
@@ -227,10 +308,10 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
   const int u = blockIdx.z * NW + w;                        // this warp's variable index
   const bool has_c = u < C, has_d = u < D, jon = j < N;
   const int bin_d = (Vmax + 1) * 32;
-  float *bd = bins + (size_t)w * bin_d;
-  for (int t = lane; t < bin_d; t += 32) bd[t] = 0.f;
+  float *bd = bins + (size_t)w * bin_d + lane;
+  for (int t = 0; t <= Vmax; ++t) bd[t * 32] = 0.f;
 
-  u64 s2[KP], m2[KP], cc2[KP], S0[KP], S1[KP], S2[KP];
+  StatRegs<KP> q;
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     float v[6];
@@ -243,76 +324,48 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
       v[2 + h] = on ? a.tb.gm[o] : 0.f;
       v[4 + h] = on ? a.tb.gc[o] : -INFINITY;
     }
-    s2[kp] = pk(v[0], v[1]); m2[kp] = pk(v[2], v[3]); cc2[kp] = pk(v[4], v[5]);
-    S0[kp] = S1[kp] = S2[kp] = 0ull;
+    q.s2[kp] = pk(v[0], v[1]); q.m2[kp] = pk(v[2], v[3]); q.cc2[kp] = pk(v[4], v[5]);
+    q.S0[kp] = q.S1[kp] = q.S2[kp] = 0ull;
   }
   float gs = 0.f;
-  const u64 neg1 = pk(-1.f, -1.f);
   // contiguous slab of points per CTA column, aligned to 32 so x / symbol loads stay coalesced
-  const int64_t per = ((a.np + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
-  const int64_t pb = (int64_t)blockIdx.x * per;
-  const int64_t pe = pb + per < a.np ? pb + per : a.np;
+  const int per = ((a.np + (int)gridDim.x - 1) / (int)gridDim.x + 31) / 32 * 32;
+  const int pb = (int)blockIdx.x * per;
+  const int pe = pb + per < a.np ? pb + per : a.np;
   const float *xcol = a.dv.cont + (int64_t)(has_c ? u : 0) * a.dv.P + a.p0;
   const uint8_t *dcol = a.dv.disc + (int64_t)(has_d ? u : 0) * a.dv.P + a.p0;
   const float *gcol = a.GA + (jon ? j : 0);
+  const int gstep = PG * N;                                 // floats between consecutive warp steps
   int inwin = 0;
-  for (int64_t base = pb; base < pe; base += 32) {
+  for (int base = pb; base < pe; base += 32) {
+    const bool full = base + 32 <= pe;
     float xreg = 0.f;
     int vreg = Vmax;
-    if (base + lane < pe) {
+    if (full || base + lane < pe) {
       if (has_c) xreg = __ldg(xcol + base + lane);
       if (has_d) vreg = (int)__ldg(dcol + base + lane);
     }
     vreg = vreg < Vmax ? vreg : Vmax;
-    for (int blk = 0; blk < LG; blk += SPB) {              // LG steps of PG points cover the 32 points
+    const float *gp = gcol + (int64_t)(base + lp) * N;      // posterior of this lane's state, step 0
+    for (int blk = 0; blk < LG; blk += SPB) {               // LG steps of PG points cover the 32 points
       float g[SPB];
+      if (full && jon && blk + SPB <= LG) {
 #pragma unroll
-      for (int i = 0; i < SPB; ++i) {
-        const int64_t p = base + (blk + i) * PG + lp;
-        g[i] = (blk + i < LG && p < pe && jon) ? __ldg(gcol + p * N) : 0.f;
+        for (int i = 0; i < SPB; ++i) g[i] = __ldg(gp + i * gstep);
+      } else {
+#pragma unroll
+        for (int i = 0; i < SPB; ++i)
+          g[i] = (blk + i < LG && base + (blk + i) * PG + lp < pe && jon) ? __ldg(gp + i * gstep) : 0.f;
       }
+      gp += SPB * gstep;
 #pragma unroll
       for (int i = 0; i < SPB; ++i) {
         if (blk + i >= LG) break;
         const int qp = (blk + i) * PG + lp;
-        if (has_c) {
-          const float x = __shfl_sync(0xffffffffu, xreg, qp);
-          const u64 xx = pk(x, x);
-          u64 e2[KP], z2[KP], zz2[KP], sum2 = 0ull;
-          float mx = -INFINITY;
-#pragma unroll
-          for (int kp = 0; kp < KP; ++kp) {
-            z2[kp] = fma2(xx, s2[kp], m2[kp]);
-            zz2[kp] = mul2(z2[kp], z2[kp]);
-            const u64 a2 = fma2(zz2[kp], neg1, cc2[kp]);
-            mx = max3lohi(mx, a2);
-            e2[kp] = ex2_2(a2);
-            sum2 = add2(sum2, e2[kp]);
-          }
-          float sum = hsum(sum2);
-          if (sum < 1e-30f && mx != -INFINITY) {           // all components underflowed: redo shifted
-            const u64 nm = pk(-mx, -mx);
-            sum2 = 0ull;
-#pragma unroll
-            for (int kp = 0; kp < KP; ++kp) {
-              e2[kp] = ex2_2(add2(fma2(zz2[kp], neg1, cc2[kp]), nm));
-              sum2 = add2(sum2, e2[kp]);
-            }
-            sum = hsum(sum2);
-          }
-          const float inv = sum > 0.f ? g[i] * rcp_approx(sum) : 0.f;
-          const u64 inv2 = pk(inv, inv);
-#pragma unroll
-          for (int kp = 0; kp < KP; ++kp) {
-            const u64 rr = mul2(e2[kp], inv2);
-            S0[kp] = add2(S0[kp], rr);
-            S1[kp] = fma2(rr, z2[kp], S1[kp]);
-            S2[kp] = fma2(rr, zz2[kp], S2[kp]);
-          }
-        }
-        if (has_d) {                                       // categorical histogram: bins[v][lane] += gamma
+        if (has_c) stat_point<KP>(q, __shfl_sync(0xffffffffu, xreg, qp), g[i]);
+        if (has_d) {                                        // categorical histogram: bins[v][lane] += gamma
           const int v = __shfl_sync(0xffffffffu, vreg, qp);
-          bd[v * 32 + lane] += g[i];
+          bd[v * 32] += g[i];
         }
         if (u == 0) gs += g[i];
       }
@@ -325,8 +378,8 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
 #pragma unroll
         for (int kp = 0; kp < KP; ++kp) {
           float sv[2], mv[2], a0[2], a1[2], a2v[2];
-          unpk(s2[kp], sv[0], sv[1]); unpk(m2[kp], mv[0], mv[1]);
-          unpk(S0[kp], a0[0], a0[1]); unpk(S1[kp], a1[0], a1[1]); unpk(S2[kp], a2v[0], a2v[1]);
+          unpk(q.s2[kp], sv[0], sv[1]); unpk(q.m2[kp], mv[0], mv[1]);
+          unpk(q.S0[kp], a0[0], a0[1]); unpk(q.S1[kp], a1[0], a1[1]); unpk(q.S2[kp], a2v[0], a2v[1]);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int k = 2 * kp + h;
@@ -346,7 +399,7 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
               atomicAdd(a.gmm + 3 * dst + 2, m2d);
             }
           }
-          S0[kp] = S1[kp] = S2[kp] = 0ull;
+          q.S0[kp] = q.S1[kp] = q.S2[kp] = 0ull;
         }
       }
       if (u == 0) {
@@ -355,11 +408,11 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
       }
       if (has_d) {
         for (int v = 0; v < Vmax; ++v) {
-          const float b = bd[v * 32 + lane];
+          const float b = bd[v * 32];
           if (b != 0.f && jon) atomicAdd(a.cat + ((int64_t)u * N + j) * Vmax + v, (double)b);
-          bd[v * 32 + lane] = 0.f;
+          bd[v * 32] = 0.f;
         }
-        bd[Vmax * 32 + lane] = 0.f;                        // unseen-symbol row is discarded
+        bd[Vmax * 32] = 0.f;                                // unseen-symbol row is discarded
       }
     }
   }
@@ -374,7 +427,7 @@ static size_t emit_smem(const Dims &d, int KP) {
 
 bool mixture_emission_fast(const dnbc_ctx *c) {
   const int KP = (c->dm.Kmax + 1) / 2;
-  return emit_smem(c->dm, KP) <= 100 * 1024;
+  return KP <= 4 && emit_smem(c->dm, KP) <= 100 * 1024;
 }
 // the statistics sweep keeps 3K coefficients + 3K accumulators in registers and handles one
 // continuous and one discrete variable per warp
@@ -384,23 +437,36 @@ bool mixture_stats_fast(const dnbc_ctx *c) {
   return d.Kmax <= 8 && units <= 64 && (size_t)8 * (d.Vmax + 1) * 32 * sizeof(float) <= 96 * 1024;
 }
 
+template <int KP>
+static void launch_emit_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_emission_pk<KP><<<grid, 512, smem, c->stream>>>(a);
+}
+
 void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   if (np <= 0) return;
   FamTimer ft(c, FAM_EMISSION);
   const Dims &d = c->dm;
-  EmitArgs a{d, c->tables(), c->data(), p0, np, out, d.Npad < 32 ? d.Npad : 32, (d.Kmax + 1) / 2};
-  const size_t smem = emit_smem(d, a.KP);
+  const int KP = (d.Kmax + 1) / 2;
+  const int vec = (c->P % 4 == 0) && (p0 % 4 == 0);
+  EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, d.Npad < 32 ? d.Npad : 32, vec};
+  const size_t smem = emit_smem(d, KP);
   const int gy = (d.Npad + 31) / 32;
   int per_sm = (int)((200 * 1024) / (smem + 1024));
-  if (per_sm > 6) per_sm = 6;
+  if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   const int64_t group = (int64_t)EPU * (32 / a.LG);
   int64_t gx = (int64_t)c->sm_count * per_sm / gy;
-  const int64_t maxgx = ((np + group - 1) / group + 7) / 8;
+  const int64_t maxgx = ((np + group - 1) / group + 15) / 16;
   if (gx > maxgx) gx = maxgx;
   if (gx < 1) gx = 1;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_emission_pk<<<dim3((unsigned)gx, (unsigned)gy), 256, smem, c->stream>>>(a);
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  switch (KP) {
+    case 1: launch_emit_t<1>(c, a, grid, smem); break;
+    case 2: launch_emit_t<2>(c, a, grid, smem); break;
+    case 3: launch_emit_t<3>(c, a, grid, smem); break;
+    default: launch_emit_t<4>(c, a, grid, smem); break;
+  }
 }
 
 // GMM moments + categorical histograms + gamma sums in one sweep over the posteriors
@@ -413,7 +479,7 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
   if (units < 1) units = 1;
   const int NW = units > 8 ? 8 : units;
   const int gz = (units + NW - 1) / NW, gy = (d.Npad + 31) / 32;
-  StatArgs a{d, c->tables(), c->data(), p0, np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
+  StatArgs a{d, c->tables(), c->data(), p0, (int)np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
              c->d_stats + sl.gamma, d.Npad < 32 ? d.Npad : 32, NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
   int64_t gx = (int64_t)c->sm_count * 2 * (8 / NW > 4 ? 4 : 8 / NW) / ((int64_t)gy * gz);
