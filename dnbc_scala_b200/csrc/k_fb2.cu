@@ -6,7 +6,7 @@
 // and are checked against the fp64 oracle (oracle/dnbc_oracle.c fb_one) and, through the
 // clamped-label bridge test, against the reference's supervised counts.
 //
-// Mapping: a group of LG = min(32, Npad) lanes owns SQ = 2 sequences at a time (two
+// Mapping: a group of LG = min(32, Npad) lanes owns SQ = 4 sequences at a time (four
 // independent dependency chains per lane); lane l holds states l, l + LG (R per lane).
 //   forward : lane keeps COLUMN j of A (alpha_t(j) = b_t(j) sum_i alpha_{t-1}(i) a_ij)
 //   backward: lane keeps ROW i of A    (beta_t(i) = sum_j a_ij u_t(j))
@@ -52,35 +52,52 @@ struct Fb2Args {
 
 constexpr int FB_WARPS = 4;
 
-// dot products of the shared vector with this lane's R matrix lines (4 partial sums per line)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float hsum2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+  return lo + hi;
+}
+
+// dot products of the shared vector with this lane's R matrix lines.  The matrix lines are
+// held as packed pairs over the reduction index, so one FFMA2 does two multiply-adds and one
+// broadcast LDS.128 feeds two of them (two independent partial sums per line).
 template <int NP, int R>
-__device__ __forceinline__ void matvec(const float *vec, const float (&M)[R][NP], float (&out)[R]) {
-  float part[R][4];
+__device__ __forceinline__ void matvec(const float *vec, const u64 (&M)[R][(NP + 1) / 2], float (&out)[R]) {
+  u64 part[R][2];
 #pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) part[r][q] = 0.f;
+  for (int r = 0; r < R; ++r) part[r][0] = part[r][1] = 0ull;
   if (NP % 4 == 0) {
     const float4 *v4 = (const float4 *)vec;
 #pragma unroll
     for (int i4 = 0; i4 < NP / 4; ++i4) {
       const float4 v = v4[i4];
+      const u64 v01 = pk2(v.x, v.y), v23 = pk2(v.z, v.w);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        part[r][0] = fmaf(v.x, M[r][4 * i4 + 0], part[r][0]);
-        part[r][1] = fmaf(v.y, M[r][4 * i4 + 1], part[r][1]);
-        part[r][2] = fmaf(v.z, M[r][4 * i4 + 2], part[r][2]);
-        part[r][3] = fmaf(v.w, M[r][4 * i4 + 3], part[r][3]);
+        part[r][0] = ffma2(v01, M[r][2 * i4], part[r][0]);
+        part[r][1] = ffma2(v23, M[r][2 * i4 + 1], part[r][1]);
       }
     }
-  } else {
+  } else {                                                   // NP == 2
+    const float2 v = *(const float2 *)vec;
 #pragma unroll
-    for (int i = 0; i < NP; ++i)
-#pragma unroll
-      for (int r = 0; r < R; ++r) part[r][i & 3] = fmaf(vec[i], M[r][i], part[r][i & 3]);
+    for (int r = 0; r < R; ++r) part[r][0] = ffma2(pk2(v.x, v.y), M[r][0], part[r][0]);
   }
 #pragma unroll
-  for (int r = 0; r < R; ++r) out[r] = (part[r][0] + part[r][1]) + (part[r][2] + part[r][3]);
+  for (int r = 0; r < R; ++r) out[r] = hsum2(part[r][0], part[r][1]);
 }
 
 // ---- forward: alpha^_t(j) = b~_t(j) sum_i alpha^_{t-1}(i) a_ij / c_t ;  LL += ln c_t + m_t
@@ -91,14 +108,19 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
   const int N = a.dm.N, Npad = a.dm.Npad;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
   const unsigned mask = gmask<LG>();
-  float Acol[R][NP], pi[R];
+  u64 Acol[R][(NP + 1) / 2];
+  float pi[R];
   int jr[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     jr[r] = lj + LG * r;
     pi[r] = jr[r] < N ? a.tb.pi[jr[r]] : 0.f;
 #pragma unroll
-    for (int i = 0; i < NP; ++i) Acol[r][i] = (i < N && jr[r] < N) ? a.tb.A[i * Npad + jr[r]] : 0.f;
+    for (int i = 0; i < NP; i += 2) {
+      const float lo = (i < N && jr[r] < N) ? a.tb.A[i * Npad + jr[r]] : 0.f;
+      const float hi = (i + 1 < N && jr[r] < N) ? a.tb.A[(i + 1) * Npad + jr[r]] : 0.f;
+      Acol[r][i / 2] = pk2(lo, hi);
+    }
   }
   const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;
   const int64_t gid = ((int64_t)blockIdx.x * FB_WARPS + w) * PG + gi;
@@ -121,48 +143,65 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
       }
     }
     for (int t = 0; t < Tmax; ++t) {
+      // phases run over all SQ sequences so their dependency chains interleave; only the two
+      // __syncwarp()s around the shared-memory exchange order the instruction stream
+      float e[SQ][R], m[SQ], acc[SQ][R], csum[SQ];
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          e[q][r] = en[q][r];
+          en[q][r] = (t + 1 < T[q] && jr[r] < N) ? a.E[row[q] + (int64_t)(t + 1) * N + jr[r]] : -INFINITY;
+        }
+        m[q] = e[q][0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) m[q] = fmaxf(m[q], e[q][r]);
+      }
+#pragma unroll
+      for (int o = LG / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) m[q] = fmaxf(m[q], __shfl_xor_sync(mask, m[q], o, LG));
+      if (t == 0) {
+#pragma unroll
+        for (int q = 0; q < SQ; ++q)
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[q][r] = pi[r];
+      } else {
+#pragma unroll
+        for (int q = 0; q < SQ; ++q)
+#pragma unroll
+          for (int r = 0; r < R; ++r) sv[w][gi][q][jr[r]] = alpha[q][r];
+        __syncwarp(mask);
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) matvec<NP, R>(sv[w][gi][q], Acol, acc[q]);
+        __syncwarp(mask);
+      }
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        if (m[q] == -INFINITY) m[q] = 0.f;
+        csum[q] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[q][r] *= ex2_approx((e[q][r] - m[q]) * (float)DNBC_LOG2E);
+          csum[q] += acc[q][r];
+        }
+      }
+#pragma unroll
+      for (int o = LG / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) csum[q] += __shfl_xor_sync(mask, csum[q], o, LG);
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         const bool live = t < T[q];
-        float e[R];
+        const float inv = rcp_approx(csum[q]);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          e[r] = en[q][r];
-          en[q][r] = (t + 1 < T[q] && jr[r] < N) ? a.E[row[q] + (int64_t)(t + 1) * N + jr[r]] : -INFINITY;
-        }
-        float m = e[0];
-#pragma unroll
-        for (int r = 1; r < R; ++r) m = fmaxf(m, e[r]);
-        m = gmax<LG>(m, mask);
-        if (m == -INFINITY) m = 0.f;
-        float acc[R];
-        if (t == 0) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = pi[r];
-        } else {
-          float *vec = sv[w][gi][q];
-#pragma unroll
-          for (int r = 0; r < R; ++r) vec[jr[r]] = alpha[q][r];
-          __syncwarp(mask);
-          matvec<NP, R>(vec, Acol, acc);
-          __syncwarp(mask);
-        }
-        float csum = 0.f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          acc[r] *= ex2_approx((e[r] - m) * (float)DNBC_LOG2E);
-          csum += acc[r];
-        }
-        csum = gsum<LG>(csum, mask);
-        const float inv = 1.0f / csum;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          alpha[q][r] = acc[r] * inv;
+          alpha[q][r] = acc[q][r] * inv;
           if (live && jr[r] < N) a.AL[row[q] + (int64_t)t * N + jr[r]] = alpha[q][r];
         }
         if (live && lj == 0) {
-          a.cs[pt[q] + t] = csum;
-          ll += (double)logf(csum) + (double)m;
+          a.cs[pt[q] + t] = csum[q];
+          ll += (double)(lg2_approx(csum[q]) * (float)DNBC_LN2) + (double)m[q];
         }
       }
     }
@@ -179,7 +218,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
   const int N = a.dm.N, Npad = a.dm.Npad;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
   const unsigned mask = gmask<LG>();
-  float Arow[R][NP];
+  u64 Arow[R][(NP + 1) / 2];
   int ir[R];
   double piacc[R];
 #pragma unroll
@@ -187,7 +226,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
     ir[r] = lj + LG * r;
     piacc[r] = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < NP; ++jj) Arow[r][jj] = (jj < N && ir[r] < N) ? a.tb.A[ir[r] * Npad + jj] : 0.f;
+    for (int jj = 0; jj < NP; jj += 2) {
+      const float lo = (jj < N && ir[r] < N) ? a.tb.A[ir[r] * Npad + jj] : 0.f;
+      const float hi = (jj + 1 < N && ir[r] < N) ? a.tb.A[ir[r] * Npad + jj + 1] : 0.f;
+      Arow[r][jj / 2] = pk2(lo, hi);
+    }
   }
   const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;
   const int64_t gid = ((int64_t)blockIdx.x * FB_WARPS + w) * PG + gi;
@@ -212,48 +255,61 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
     }
     // sequences of a pair are aligned at their LAST step: step index k counts back from it
     for (int k = 0; k < Tmax; ++k) {
+      float al[SQ][R], e[SQ][R], m[SQ], cn[SQ];
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         const int t = T[q] - 1 - k;
-        const bool live = t >= 0;
-        float al[R], e[R];
-        const float c_next = csn[q];
+        cn[q] = csn[q];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          al[r] = aln[q][r];
-          e[r] = en[q][r];
+          al[q][r] = aln[q][r];
+          e[q][r] = en[q][r];
           // prefetch for step t-1: alpha_{t-1}, and E_t / c_t (the "t+1" quantities of step t-1)
           aln[q][r] = (t > 0 && ir[r] < N) ? a.AL[row[q] + (int64_t)(t - 1) * N + ir[r]] : 0.f;
           en[q][r] = (t > 0 && ir[r] < N) ? a.E[row[q] + (int64_t)t * N + ir[r]] : -INFINITY;
         }
         csn[q] = t > 0 ? a.cs[pt[q] + t] : 1.f;
-        if (k > 0) {
-          float m = e[0];
+        m[q] = e[q][0];
 #pragma unroll
-          for (int r = 1; r < R; ++r) m = fmaxf(m, e[r]);
-          m = gmax<LG>(m, mask);
-          if (m == -INFINITY) m = 0.f;
-          const float ic = 1.0f / c_next;
-          float *vec = sv[w][gi][q];
-          float u[R];
+        for (int r = 1; r < R; ++r) m[q] = fmaxf(m[q], e[q][r]);
+      }
+      if (k > 0) {
+#pragma unroll
+        for (int o = LG / 2; o > 0; o >>= 1)
+#pragma unroll
+          for (int q = 0; q < SQ; ++q) m[q] = fmaxf(m[q], __shfl_xor_sync(mask, m[q], o, LG));
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) {
+          const int t = T[q] - 1 - k;
+          if (m[q] == -INFINITY) m[q] = 0.f;
+          const float ic = rcp_approx(cn[q]);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            u[r] = ex2_approx((e[r] - m) * (float)DNBC_LOG2E) * beta[q][r] * ic;
-            if (live && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = u[r];
-            vec[ir[r]] = u[r];
+            const float u = ex2_approx((e[q][r] - m[q]) * (float)DNBC_LOG2E) * beta[q][r] * ic;
+            if (t >= 0 && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = u;
+            sv[w][gi][q][ir[r]] = u;
           }
-          __syncwarp(mask);
-          matvec<NP, R>(vec, Arow, beta[q]);
-          __syncwarp(mask);
-        } else if (live) {
+        }
+        __syncwarp(mask);
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) matvec<NP, R>(sv[w][gi][q], Arow, beta[q]);
+        __syncwarp(mask);
+      } else {
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) {
+          const int t = T[q] - 1;
 #pragma unroll
           for (int r = 0; r < R; ++r)
-            if (ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = 0.f;
+            if (t >= 0 && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = 0.f;
         }
+      }
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        const int t = T[q] - 1 - k;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float g = al[r] * beta[q][r];
-          if (live && ir[r] < N) a.GA[row[q] + (int64_t)t * N + ir[r]] = g;
+          const float g = al[q][r] * beta[q][r];
+          if (t >= 0 && ir[r] < N) a.GA[row[q] + (int64_t)t * N + ir[r]] = g;
           if (t == 0) piacc[r] += (double)g;
         }
       }
@@ -266,7 +322,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
 
 template <int LG, int R>
 static void launch_fb2_t(dnbc_ctx *c, const Fb2Args &a, bool backward) {
-  constexpr int SQ = 2, PG = 32 / LG;
+  constexpr int SQ = 4, PG = 32 / LG;
   const int64_t nseq = a.s1 - a.s0;
   const int64_t per_block = (int64_t)FB_WARPS * PG * SQ;
   int64_t blocks = (nseq + per_block - 1) / per_block;

@@ -201,33 +201,51 @@ __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
         for (int i = 0; i < EPU; ++i) x[i] = po[i] < a.np ? __ldg(col + po[i]) : 0.f;
       }
     };
+    // symbols of discrete variable d for this lane's EPU points, packed one byte per point
+    auto load_v = [&](int d) -> uint32_t {
+      const uint8_t *col = disc0 + (int64_t)d * P;
+      if (vec && full) return __ldg((const uint32_t *)(col + pb));
+      uint32_t w4 = 0;
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) w4 |= (po[i] < a.np ? (uint32_t)__ldg(col + po[i]) : (uint32_t)Vmax) << (8 * i);
+      return w4;
+    };
+    auto add_cat = [&](const float *tab, uint32_t w4) {
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) {
+        const int v = (int)((w4 >> (8 * i)) & 0xffu);
+        acc[i] += tab[(v < Vmax ? v : Vmax) * 32];
+      }
+    };
+    // variable c + 1's observations (and discrete variable c + 1's symbols) are fetched while
+    // variable c is evaluated, so no load latency is exposed
     float xc[EPU], xn[EPU];
+    uint32_t vc = 0, vn = 0;
     if (C > 0) load_x(0, xc);
+    if (D > 0) vc = load_v(0);
     const float4 *ps = sm_sm + lane;
     const float2 *pc = sm_cc + lane;
+    const float *tab = sm_cat + lane;
+    const int tstride = (Vmax + 1) * 32;
     for (int c = 0; c < C; ++c) {
       if (c + 1 < C) load_x(c + 1, xn);
+      if (c + 1 < D) vn = load_v(c + 1);
       emit_var<KP>(ps, pc, xc, acc);
       ps += cstride;
       pc += cstride;
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) xc[i] = xn[i];
-    }
-    const float *tab = sm_cat + lane;
-    for (int d = 0; d < D; ++d) {
-      const uint8_t *col = disc0 + (int64_t)d * P;
-      int v[EPU];
-      if (vec && full) {
-        const uint32_t w4 = __ldg((const uint32_t *)(col + pb));
-#pragma unroll
-        for (int i = 0; i < EPU; ++i) v[i] = (int)((w4 >> (8 * i)) & 0xffu);
-      } else {
-#pragma unroll
-        for (int i = 0; i < EPU; ++i) v[i] = po[i] < a.np ? (int)__ldg(col + po[i]) : Vmax;
+      if (c < D) {
+        add_cat(tab, vc);
+        tab += tstride;
       }
 #pragma unroll
-      for (int i = 0; i < EPU; ++i) acc[i] += tab[(v[i] < Vmax ? v[i] : Vmax) * 32];
-      tab += (Vmax + 1) * 32;
+      for (int i = 0; i < EPU; ++i) xc[i] = xn[i];
+      vc = vn;
+    }
+    for (int d = C; d < D; ++d) {                           // more discrete than continuous variables
+      if (d + 1 < D) vn = load_v(d + 1);
+      add_cat(tab, vc);
+      tab += tstride;
+      vc = vn;
     }
     if (j < N) {
       float *dst = a.E + (int64_t)pb * N + j;
@@ -260,41 +278,69 @@ struct StatRegs {
   u64 s2[KP], m2[KP], cc2[KP], S0[KP], S1[KP], S2[KP];
 };
 
-// one point: responsibilities of this warp's variable, weighted by the posterior g
+// one point: responsibilities of this warp's variable, weighted by the posterior g.
+// Branch-free: exponents are shifted by their maximum before ex2, so the mixture sum is >= 1
+// whenever any component has mass (no fp32 underflow, no fallback path) and consecutive points
+// interleave freely in the instruction stream.
 template <int KP>
 __device__ __forceinline__ void stat_point(StatRegs<KP> &q, float x, float g) {
   const u64 neg1 = pk(-1.f, -1.f);
   const u64 xx = pk(x, x);
-  u64 e2[KP], z2[KP], zz2[KP], sum2 = 0ull;
+  u64 a2[KP], z2[KP], zz2[KP];
   float mx = -INFINITY;
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     z2[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
     zz2[kp] = mul2(z2[kp], z2[kp]);
-    const u64 a2 = fma2(zz2[kp], neg1, q.cc2[kp]);
-    mx = max3lohi(mx, a2);
-    e2[kp] = ex2_2(a2);
-    sum2 = add2(sum2, e2[kp]);
+    a2[kp] = fma2(zz2[kp], neg1, q.cc2[kp]);
+    mx = max3lohi(mx, a2[kp]);
   }
-  float sum = hsum(sum2);
-  if (sum < 1e-30f && mx != -INFINITY) {                   // all components underflowed: redo shifted
-    const u64 nm = pk(-mx, -mx);
-    sum2 = 0ull;
+  mx = mx == -INFINITY ? 0.f : mx;                          // no component has mass: e = 0, sum = 0
+  const u64 nm = pk(-mx, -mx);
+  u64 sum2 = 0ull;
 #pragma unroll
-    for (int kp = 0; kp < KP; ++kp) {
-      e2[kp] = ex2_2(add2(fma2(zz2[kp], neg1, q.cc2[kp]), nm));
-      sum2 = add2(sum2, e2[kp]);
-    }
-    sum = hsum(sum2);
+  for (int kp = 0; kp < KP; ++kp) {
+    a2[kp] = ex2_2(add2(a2[kp], nm));
+    sum2 = add2(sum2, a2[kp]);
   }
+  const float sum = hsum(sum2);
   const float inv = sum > 0.f ? g * rcp_approx(sum) : 0.f;
   const u64 inv2 = pk(inv, inv);
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
-    const u64 rr = mul2(e2[kp], inv2);
+    const u64 rr = mul2(a2[kp], inv2);
     q.S0[kp] = add2(q.S0[kp], rr);
     q.S1[kp] = fma2(rr, z2[kp], q.S1[kp]);
     q.S2[kp] = fma2(rr, zz2[kp], q.S2[kp]);
+  }
+}
+
+// 32 points: the warp-uniform role flags are template parameters so the inner loop carries no
+// per-point branches
+template <int KP, bool HAS_C, bool HAS_D, bool GSUM>
+__device__ __forceinline__ void stat_block(StatRegs<KP> &q, float &gs, float *bd, const float *gp, int gstep, float xreg,
+                                           int vreg, int LG, int PG, int lp, bool fast, int base, int pe, bool jon) {
+  for (int blk = 0; blk < LG; blk += SPB) {                 // LG steps of PG points cover the 32 points
+    float g[SPB];
+    if (fast && blk + SPB <= LG) {
+#pragma unroll
+      for (int i = 0; i < SPB; ++i) g[i] = __ldg(gp + i * gstep);
+    } else {
+#pragma unroll
+      for (int i = 0; i < SPB; ++i)
+        g[i] = (blk + i < LG && base + (blk + i) * PG + lp < pe && jon) ? __ldg(gp + i * gstep) : 0.f;
+    }
+    gp += SPB * gstep;
+#pragma unroll
+    for (int i = 0; i < SPB; ++i) {
+      const int qp = (blk + i) * PG + lp;                    // (steps past LG read lane qp & 31: g is 0 there)
+      if (HAS_C) stat_point<KP>(q, __shfl_sync(0xffffffffu, xreg, qp), g[i]);
+      if (HAS_D) {                                           // categorical histogram: bins[v][lane] += gamma
+        const int v = __shfl_sync(0xffffffffu, vreg, qp);
+        bd[v * 32] += g[i];
+      }
+      if (GSUM) gs += g[i];
+    }
   }
 }
 
@@ -347,29 +393,13 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
     }
     vreg = vreg < Vmax ? vreg : Vmax;
     const float *gp = gcol + (int64_t)(base + lp) * N;      // posterior of this lane's state, step 0
-    for (int blk = 0; blk < LG; blk += SPB) {               // LG steps of PG points cover the 32 points
-      float g[SPB];
-      if (full && jon && blk + SPB <= LG) {
-#pragma unroll
-        for (int i = 0; i < SPB; ++i) g[i] = __ldg(gp + i * gstep);
-      } else {
-#pragma unroll
-        for (int i = 0; i < SPB; ++i)
-          g[i] = (blk + i < LG && base + (blk + i) * PG + lp < pe && jon) ? __ldg(gp + i * gstep) : 0.f;
-      }
-      gp += SPB * gstep;
-#pragma unroll
-      for (int i = 0; i < SPB; ++i) {
-        if (blk + i >= LG) break;
-        const int qp = (blk + i) * PG + lp;
-        if (has_c) stat_point<KP>(q, __shfl_sync(0xffffffffu, xreg, qp), g[i]);
-        if (has_d) {                                        // categorical histogram: bins[v][lane] += gamma
-          const int v = __shfl_sync(0xffffffffu, vreg, qp);
-          bd[v * 32] += g[i];
-        }
-        if (u == 0) gs += g[i];
-      }
-    }
+    const bool fast = full && jon;
+#define STAT_BLOCK(C_, D_, G_) stat_block<KP, C_, D_, G_>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, fast, base, pe, jon)
+    if (has_c && has_d) { if (u == 0) STAT_BLOCK(true, true, true); else STAT_BLOCK(true, true, false); }
+    else if (has_c) { if (u == 0) STAT_BLOCK(true, false, true); else STAT_BLOCK(true, false, false); }
+    else if (has_d) { if (u == 0) STAT_BLOCK(false, true, true); else STAT_BLOCK(false, true, false); }
+    else if (u == 0) STAT_BLOCK(false, false, true);
+#undef STAT_BLOCK
     inwin += 32;
     if (inwin >= a.window || base + 32 >= pe) {
       inwin = 0;
