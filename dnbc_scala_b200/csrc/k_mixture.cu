@@ -271,7 +271,7 @@ struct StatArgs {
   int LG, NW, window;
 };
 
-constexpr int SPB = 8;   // points whose posteriors are fetched together (memory-level parallelism)
+constexpr int SPB = 4;   // points whose posteriors are fetched together, one group ahead of their use
 
 template <int KP>
 struct StatRegs {
@@ -316,21 +316,30 @@ __device__ __forceinline__ void stat_point(StatRegs<KP> &q, float x, float g) {
 }
 
 // 32 points: the warp-uniform role flags are template parameters so the inner loop carries no
-// per-point branches
+// per-point branches.  Posteriors are fetched SPB points ahead (gn) of the ones being consumed.
+// (A two-phase software pipeline across points was tried and was slower: it adds fp32 work to
+// a loop that is bound by register-file read bandwidth, see DESIGN.md.)
 template <int KP, bool HAS_C, bool HAS_D, bool GSUM>
 __device__ __forceinline__ void stat_block(StatRegs<KP> &q, float &gs, float *bd, const float *gp, int gstep, float xreg,
                                            int vreg, int LG, int PG, int lp, bool fast, int base, int pe, bool jon) {
-  for (int blk = 0; blk < LG; blk += SPB) {                 // LG steps of PG points cover the 32 points
-    float g[SPB];
+  float gn[SPB];
+  auto fetch = [&](int blk) {
     if (fast && blk + SPB <= LG) {
 #pragma unroll
-      for (int i = 0; i < SPB; ++i) g[i] = __ldg(gp + i * gstep);
+      for (int i = 0; i < SPB; ++i) gn[i] = __ldg(gp + i * gstep);
     } else {
 #pragma unroll
       for (int i = 0; i < SPB; ++i)
-        g[i] = (blk + i < LG && base + (blk + i) * PG + lp < pe && jon) ? __ldg(gp + i * gstep) : 0.f;
+        gn[i] = (blk + i < LG && base + (blk + i) * PG + lp < pe && jon) ? __ldg(gp + i * gstep) : 0.f;
     }
     gp += SPB * gstep;
+  };
+  fetch(0);
+  for (int blk = 0; blk < LG; blk += SPB) {                 // LG steps of PG points cover the 32 points
+    float g[SPB];
+#pragma unroll
+    for (int i = 0; i < SPB; ++i) g[i] = gn[i];
+    if (blk + SPB < LG) fetch(blk + SPB);
 #pragma unroll
     for (int i = 0; i < SPB; ++i) {
       const int qp = (blk + i) * PG + lp;                    // (steps past LG read lane qp & 31: g is 0 there)
@@ -383,15 +392,23 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
   const float *gcol = a.GA + (jon ? j : 0);
   const int gstep = PG * N;                                 // floats between consecutive warp steps
   int inwin = 0;
+  // the observation / symbol of point base + lane, fetched one 32-point block ahead
+  float xnext = 0.f;
+  int vnext = Vmax;
+  if (pb + lane < pe) {
+    if (has_c) xnext = __ldg(xcol + pb + lane);
+    if (has_d) vnext = (int)__ldg(dcol + pb + lane);
+  }
   for (int base = pb; base < pe; base += 32) {
     const bool full = base + 32 <= pe;
-    float xreg = 0.f;
-    int vreg = Vmax;
-    if (full || base + lane < pe) {
-      if (has_c) xreg = __ldg(xcol + base + lane);
-      if (has_d) vreg = (int)__ldg(dcol + base + lane);
+    const float xreg = xnext;
+    const int vreg = vnext < Vmax ? vnext : Vmax;
+    xnext = 0.f;
+    vnext = Vmax;
+    if (base + 32 + lane < pe) {
+      if (has_c) xnext = __ldg(xcol + base + 32 + lane);
+      if (has_d) vnext = (int)__ldg(dcol + base + 32 + lane);
     }
-    vreg = vreg < Vmax ? vreg : Vmax;
     const float *gp = gcol + (int64_t)(base + lp) * N;      // posterior of this lane's state, step 0
     const bool fast = full && jon;
 #define STAT_BLOCK(C_, D_, G_) stat_block<KP, C_, D_, G_>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, fast, base, pe, jon)
