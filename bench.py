@@ -159,6 +159,8 @@ def run_b200(args, wl):
         raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the single JSON line (NCCL prints its version banner there at VERSION/INFO)
+        os.environ["NCCL_DEBUG"] = os.environ.get("DNBC_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
     seqs = args.seqs or max(1, wl.S // 8)
