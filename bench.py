@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     return ap.parse_args()
 
 
@@ -222,6 +223,17 @@ def run_b200(args, wl):
     ll_after = float(ctx.em_get_stats()[0])
     value = units_per_step * args.steps / (ms * 1e-3)
 
+    # ---- second BASELINE metric: Viterbi sequences / s (decode of the resident shard, paths
+    #      downloaded to the host; upload excluded) ------------------------------------------
+    decode = None
+    if not args.no_decode:
+        def decode_step():
+            ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32, want_score=True, want_tie=False)
+        ms_d, _, _ = timed(decode_step, 2, 1)
+        decode = {"metric": "viterbi_sequences_per_sec", "value": total_seqs * 2 / (ms_d * 1e-3), "unit": "sequences/s",
+                  "mode": "BACKTRACE (true Viterbi, on-device back-trace), f32", "seq_len": wl.T,
+                  "ms_per_pass": ms_d / 2, "d2h_bytes_per_pass": int(seqs * wl.T * 2 + seqs * 8)}
+
     # ---- end to end through the C ABI with host buffers ("e2e") --------------------
     e2e = None
     if not args.no_e2e:
@@ -233,8 +245,10 @@ def run_b200(args, wl):
         out = {}
 
         def e2e_step():
-            ctx.upload_raw(seqs, off, h_disc.data_ptr() if wl.D else 0, h_cont.data_ptr() if wl.C else 0)
-            step()
+            # upload of chunk k+1 overlaps the kernels of chunk k (dnbc_em_estep_streamed)
+            ctx.em_estep_streamed_raw(seqs, off, h_disc.data_ptr() if wl.D else 0, h_cont.data_ptr() if wl.C else 0)
+            allreduce()
+            ctx.em_mstep(total_seqs)
             out["params"] = ctx.get_params()            # learned parameters back on the host
             out["ll"] = float(ctx.em_get_stats()[0])    # and the iteration's log-likelihood
 
@@ -284,7 +298,7 @@ def run_b200(args, wl):
             "fp32": {"algorithmic_tflops_per_gpu": fp32_tflops, "nominal_peak_tflops": 74.4,
                      "frac_of_nominal": fp32_tflops / 74.4, "flops_per_timestep": wl.flops_per_timestep},
             "kernel_ms_per_step": {k: v / args.steps for k, v in fam_ms.items()},
-            "loglik_after": ll_after,
+            "loglik_after": ll_after, "decode": decode,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

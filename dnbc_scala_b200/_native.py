@@ -28,7 +28,7 @@ SYMBOLS = (
     "dnbc_abi_version", "dnbc_create", "dnbc_destroy", "dnbc_last_error", "dnbc_set_params",
     "dnbc_get_params", "dnbc_upload", "dnbc_generate", "dnbc_download", "dnbc_download_f32", "dnbc_data_shape",
     "dnbc_emission_logprob", "dnbc_supervised_counts", "dnbc_mle", "dnbc_stats_size",
-    "dnbc_em_estep", "dnbc_em_stats_device_ptr", "dnbc_em_get_stats", "dnbc_em_set_stats",
+    "dnbc_em_estep", "dnbc_em_estep_streamed", "dnbc_em_stats_device_ptr", "dnbc_em_get_stats", "dnbc_em_set_stats",
     "dnbc_em_mstep", "dnbc_em_iterate", "dnbc_em_get_posteriors", "dnbc_decode",
     "dnbc_synchronize", "dnbc_stream", "dnbc_launch_count", "dnbc_profile_enable",
     "dnbc_profile_read",
@@ -87,6 +87,7 @@ def lib():
         L.dnbc_stats_size.argtypes = [vp]
         L.dnbc_stats_size.restype = i64
         L.dnbc_em_estep.argtypes = [vp, i32]
+        L.dnbc_em_estep_streamed.argtypes = [vp, i64, vp, vp, vp, vp, i32]
         L.dnbc_em_stats_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.dnbc_em_get_stats.argtypes = [vp, vp]
         L.dnbc_em_set_stats.argtypes = [vp, vp]
@@ -235,6 +236,24 @@ class Context:
 
     def em_estep(self, clamp_labels: bool = False):
         self._check(lib().dnbc_em_estep(self._h, int(clamp_labels)))
+
+    def em_estep_streamed_raw(self, n_seq: int, offsets: np.ndarray, disc_ptr: int, cont32_ptr: int,
+                              labels_ptr: int = 0, clamp_labels: bool = False):
+        """Upload (from raw, ideally pinned, host addresses) overlapped with the E-step."""
+        off = np.ascontiguousarray(offsets, np.int64)
+        self._check(lib().dnbc_em_estep_streamed(self._h, int(n_seq), _p(off), disc_ptr or None, cont32_ptr or None,
+                                                 labels_ptr or None, int(clamp_labels)))
+        self.S, self.P = int(n_seq), int(off[-1])
+
+    def em_estep_streamed(self, offsets, disc, cont32, labels=None, clamp_labels: bool = False):
+        off = np.ascontiguousarray(offsets, np.int64)
+        P = int(off[-1])
+        d = np.ascontiguousarray(disc, np.uint8).reshape(self.D, P) if self.D else None
+        c = np.ascontiguousarray(cont32, np.float32).reshape(self.C, P) if self.C else None
+        lab = None if labels is None else np.ascontiguousarray(labels, np.int32).reshape(P)
+        self._check(lib().dnbc_em_estep_streamed(self._h, len(off) - 1, _p(off), _p(d), _p(c), _p(lab), int(clamp_labels)))
+        self.synchronize()                     # numpy sources are pageable: finish before they can be freed
+        self.S, self.P = len(off) - 1, P
 
     def em_stats_device_ptr(self) -> int:
         p = C.c_void_p()

@@ -165,6 +165,8 @@ extern "C" int dnbc_destroy(dnbc_ctx *c) {
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : c->chunk_events) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -538,20 +540,16 @@ extern "C" int dnbc_mle(dnbc_ctx *c, int flags, const double *init_centroids, in
 // ---------------------------------------------------------------------------------
 extern "C" int64_t dnbc_stats_size(const dnbc_ctx *c) { return c ? c->stats_size : 0; }
 
-extern "C" int dnbc_em_estep(dnbc_ctx *c, int clamp_labels) {
-  if (!c) return DNBC_EINVAL;
-  if (clamp_labels && !c->have_labels) return dnbc_fail(c, DNBC_ESTATE, "clamped E-step needs labels");
-  CU_TRY(c, cudaSetDevice(c->device));
-  CU_TRY(c, cudaMemsetAsync(c->d_stats, 0, (size_t)c->stats_size * sizeof(double), c->stream));
-  if (c->S == 0) return DNBC_OK;
-  const int64_t maxp = chunk_budget_points(c, (size_t)c->dm.N * 4 * sizeof(float) + 4);
-  int rc = reserve_em_scratch(c, std::max(maxp, c->scratch_points));
-  if (rc) return rc;
-  for (const Chunk &ch : make_chunks(c, c->scratch_points)) {
+// E-step over the resident sequences, chunk by chunk.  When `ready` is given, chunk k first
+// waits for event ready[k] (its observations are still in flight on the copy stream).
+static int estep_chunks(dnbc_ctx *c, int clamp_labels, const std::vector<Chunk> &chunks, const std::vector<cudaEvent_t> *ready) {
+  for (size_t k = 0; k < chunks.size(); ++k) {
+    const Chunk &ch = chunks[k];
     if (ch.np > c->scratch_points) {
-      rc = reserve_em_scratch(c, ch.np);
+      int rc = reserve_em_scratch(c, ch.np);
       if (rc) return rc;
     }
+    if (ready) CU_TRY(c, cudaStreamWaitEvent(c->stream, (*ready)[k], 0));
     launch_emission_f32(c, ch.p0, ch.np, c->E);
     if (clamp_labels) launch_clamp_labels(c, ch.p0, ch.np, c->E);
     launch_forward(c, ch.s0, ch.s1, ch.p0);
@@ -566,6 +564,77 @@ extern "C" int dnbc_em_estep(dnbc_ctx *c, int clamp_labels) {
   }
   CU_TRY(c, cudaGetLastError());
   return DNBC_OK;
+}
+
+extern "C" int dnbc_em_estep(dnbc_ctx *c, int clamp_labels) {
+  if (!c) return DNBC_EINVAL;
+  if (clamp_labels && !c->have_labels) return dnbc_fail(c, DNBC_ESTATE, "clamped E-step needs labels");
+  CU_TRY(c, cudaSetDevice(c->device));
+  CU_TRY(c, cudaMemsetAsync(c->d_stats, 0, (size_t)c->stats_size * sizeof(double), c->stream));
+  if (c->S == 0) return DNBC_OK;
+  const int64_t maxp = chunk_budget_points(c, (size_t)c->dm.N * 4 * sizeof(float) + 4);
+  int rc = reserve_em_scratch(c, std::max(maxp, c->scratch_points));
+  if (rc) return rc;
+  return estep_chunks(c, clamp_labels, make_chunks(c, c->scratch_points), nullptr);
+}
+
+// Upload + E-step in one call, the host->device copy of chunk k+1 overlapping the kernels of
+// chunk k (copy stream + per-chunk events).  The observations stay resident afterwards exactly
+// as after dnbc_upload.  Host buffers should be pinned for the copies to be asynchronous.
+extern "C" int dnbc_em_estep_streamed(dnbc_ctx *c, int64_t n_seq, const int64_t *offsets, const uint8_t *disc,
+                                      const float *cont_f32, const int32_t *labels, int clamp_labels) {
+  if (!c) return DNBC_EINVAL;
+  const Dims &d = c->dm;
+  if (n_seq < 0 || !offsets || offsets[0] != 0) return dnbc_fail(c, DNBC_EINVAL, "estep_streamed: bad offsets");
+  int64_t Tmax = 0;
+  for (int64_t s = 0; s < n_seq; ++s) {
+    if (offsets[s + 1] < offsets[s]) return dnbc_fail(c, DNBC_EINVAL, "estep_streamed: offsets must be non-decreasing");
+    Tmax = std::max(Tmax, offsets[s + 1] - offsets[s]);
+  }
+  const int64_t P = offsets[n_seq];
+  if ((d.D > 0 && P > 0 && !disc) || (d.C > 0 && P > 0 && !cont_f32))
+    return dnbc_fail(c, DNBC_EINVAL, "Number of observed variables is inconsistent");   // DNBC.scala:46, :148
+  if (clamp_labels && !labels) return dnbc_fail(c, DNBC_ESTATE, "clamped E-step needs labels");
+  CU_TRY(c, cudaSetDevice(c->device));
+  int rc = reserve_points(c, n_seq, P, false, labels != nullptr);
+  if (rc) return rc;
+  c->h_off.assign(offsets, offsets + n_seq + 1);
+  c->S = n_seq; c->P = P; c->Tmax = Tmax;
+  c->have_labels = labels != nullptr;
+  c->have_cont64 = false;
+  CU_TRY(c, cudaMemcpyAsync(c->d_off, offsets, (size_t)(n_seq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemsetAsync(c->d_stats, 0, (size_t)c->stats_size * sizeof(double), c->stream));
+  if (n_seq == 0) return DNBC_OK;
+  const int64_t maxp = chunk_budget_points(c, (size_t)d.N * 4 * sizeof(float) + 4);
+  rc = reserve_em_scratch(c, std::max(maxp, c->scratch_points));
+  if (rc) return rc;
+  // finer chunks than the scratch allows shorten the un-overlapped first copy
+  const std::vector<Chunk> chunks = make_chunks(c, std::min<int64_t>(c->scratch_points, std::max<int64_t>(Tmax, (int64_t)4 << 20)));
+  if (!c->copy_stream) CU_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  while (c->chunk_events.size() < chunks.size() + 1) {
+    cudaEvent_t e;
+    CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->chunk_events.push_back(e);
+  }
+  // the copy stream must not overwrite planes that earlier kernels are still reading
+  cudaEvent_t fence = c->chunk_events[chunks.size()];
+  CU_TRY(c, cudaEventRecord(fence, c->stream));
+  CU_TRY(c, cudaStreamWaitEvent(c->copy_stream, fence, 0));
+  for (size_t k = 0; k < chunks.size(); ++k) {
+    const Chunk &ch = chunks[k];
+    for (int v = 0; v < d.D; ++v)
+      CU_TRY(c, cudaMemcpyAsync(c->d_disc + (size_t)v * P + ch.p0, disc + (size_t)v * P + ch.p0, (size_t)ch.np,
+                                cudaMemcpyHostToDevice, c->copy_stream));
+    for (int v = 0; v < d.C; ++v)
+      CU_TRY(c, cudaMemcpyAsync(c->d_cont + (size_t)v * P + ch.p0, cont_f32 + (size_t)v * P + ch.p0,
+                                (size_t)ch.np * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    if (labels)
+      CU_TRY(c, cudaMemcpyAsync(c->d_labels + ch.p0, labels + ch.p0, (size_t)ch.np * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                c->copy_stream));
+    CU_TRY(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
+  }
+  std::vector<cudaEvent_t> ready(c->chunk_events.begin(), c->chunk_events.begin() + chunks.size());
+  return estep_chunks(c, clamp_labels, chunks, &ready);
 }
 
 extern "C" int dnbc_em_stats_device_ptr(dnbc_ctx *c, void **ptr) {

@@ -51,6 +51,8 @@ struct dnbc_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;        // host->device copies overlapped with the E-step
+  std::vector<cudaEvent_t> chunk_events;
   std::string err;
   int64_t launches = 0;
 

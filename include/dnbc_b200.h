@@ -130,6 +130,12 @@ int dnbc_mle(dnbc_ctx *ctx, int flags, const double *init_centroids, int max_ite
 int64_t dnbc_stats_size(const dnbc_ctx *ctx);
 /* E-step over the resident sequences into the device statistics buffer */
 int dnbc_em_estep(dnbc_ctx *ctx, int clamp_labels);
+/* dnbc_upload + dnbc_em_estep in one call with the host->device copy of each chunk of sequences
+ * overlapping the kernels of the previous chunk (the reference materialises every sequence on
+ * the driver before learning, DynamicNaiveBayesianClassifier.scala:129-159).  The observations
+ * stay resident afterwards; host buffers should be pinned.  labels may be NULL. */
+int dnbc_em_estep_streamed(dnbc_ctx *ctx, int64_t n_seq, const int64_t *offsets, const uint8_t *disc,
+                           const float *cont_f32, const int32_t *labels, int clamp_labels);
 /* device address of the statistics buffer (for an NCCL all-reduce by the host) */
 int dnbc_em_stats_device_ptr(dnbc_ctx *ctx, void **ptr);
 int dnbc_em_get_stats(dnbc_ctx *ctx, double *stats);

@@ -266,6 +266,25 @@ def test_em_iterations_match_oracle(oracle, N, V, K, S, T):
     np.testing.assert_allclose(p["pi"], want.pi, rtol=TOL * 3, atol=1e-7)
 
 
+def test_streamed_estep_equals_upload_then_estep(oracle):
+    """dnbc_em_estep_streamed (copy of chunk k+1 overlapped with the kernels of chunk k) gives
+    the same statistics as dnbc_upload + dnbc_em_estep and leaves the data resident."""
+    m = random_model(oracle, 10, [10] * 5, [3, 1, 4, 2, 3], 54)
+    data = sample(oracle, m, [200] * 40 + [3, 1, 77], 55)
+    q = perturb(oracle, m, 56)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        ctx.em_estep()
+        want = ctx.em_get_stats()
+        ctx.em_estep_streamed(data.off, data.disc, data.cont.astype(np.float32))
+        got = ctx.em_get_stats()
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+        ctx.em_estep()                                  # data stayed resident
+        np.testing.assert_allclose(ctx.em_get_stats(), want, rtol=1e-6, atol=1e-6)
+        ref = oracle.estep(q, data)
+        assert abs(got[0] - ref[0]) <= TOL * abs(ref[0])
+
+
 def test_bridge_clamped_em_reproduces_supervised_learner(oracle):
     """One clamped EM iteration == the reference's supervised result: ties the
     Baum-Welch kernels, which have no reference counterpart, to DNBC.scala:124-220."""
