@@ -280,7 +280,8 @@ def run_b200(args, wl):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get(top)
+                tr = json.load(fh).get(top)
+                traffic = tr["bytes_per_point"] * pts_per_launch if tr else None
         except OSError:
             pass
         step_ms = ms / args.steps
