@@ -160,7 +160,7 @@ extern "C" int dnbc_destroy(dnbc_ctx *c) {
                   c->t_gm,    c->t_gc,    c->t64_logpi, c->t64_logA, c->t64_logB, c->t64_u, c->t64_rs,  c->d_off,
                   c->d_disc,  c->d_cont,  c->d_cont64, c->d_labels, c->E,      c->AL,      c->GA,       c->U,
                   c->cs,      c->d_stats, c->E64,    c->d_bp,     c->d_path,   c->d_score, c->d_tie,    c->d_cnt,
-                  c->d_first_seq, c->d_assign, c->d_edge, c->d_edge_i};
+                  c->d_first_seq, c->d_assign, c->d_edge, c->d_edge_i, c->tc_tab, c->tc_x, c->tc_mrow};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -433,6 +433,16 @@ static std::vector<Chunk> make_chunks(const dnbc_ctx *c, int64_t max_points) {
   return out;
 }
 
+// points the E-step scratch should hold: everything resident if it already fits, otherwise a
+// budget from the free memory (cudaMemGetInfo costs milliseconds, so it is only asked when the
+// scratch has to grow)
+static int64_t chunk_budget_points(const dnbc_ctx *c, size_t bytes_per_point);
+static int64_t em_scratch_target(const dnbc_ctx *c) {
+  if (c->E && c->scratch_points >= c->P) return c->scratch_points;
+  if (c->E && c->scratch_points >= ((int64_t)4 << 20) && c->scratch_points >= c->Tmax) return c->scratch_points;
+  return chunk_budget_points(c, (size_t)c->dm.N * 4 * sizeof(float) + 4);
+}
+
 static int64_t chunk_budget_points(const dnbc_ctx *c, size_t bytes_per_point) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
@@ -572,7 +582,7 @@ extern "C" int dnbc_em_estep(dnbc_ctx *c, int clamp_labels) {
   CU_TRY(c, cudaSetDevice(c->device));
   CU_TRY(c, cudaMemsetAsync(c->d_stats, 0, (size_t)c->stats_size * sizeof(double), c->stream));
   if (c->S == 0) return DNBC_OK;
-  const int64_t maxp = chunk_budget_points(c, (size_t)c->dm.N * 4 * sizeof(float) + 4);
+  const int64_t maxp = em_scratch_target(c);
   int rc = reserve_em_scratch(c, std::max(maxp, c->scratch_points));
   if (rc) return rc;
   return estep_chunks(c, clamp_labels, make_chunks(c, c->scratch_points), nullptr);
@@ -605,7 +615,7 @@ extern "C" int dnbc_em_estep_streamed(dnbc_ctx *c, int64_t n_seq, const int64_t 
   CU_TRY(c, cudaMemcpyAsync(c->d_off, offsets, (size_t)(n_seq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(c->d_stats, 0, (size_t)c->stats_size * sizeof(double), c->stream));
   if (n_seq == 0) return DNBC_OK;
-  const int64_t maxp = chunk_budget_points(c, (size_t)d.N * 4 * sizeof(float) + 4);
+  const int64_t maxp = em_scratch_target(c);
   rc = reserve_em_scratch(c, std::max(maxp, c->scratch_points));
   if (rc) return rc;
   // finer chunks than the scratch allows shorten the un-overlapped first copy

@@ -87,6 +87,11 @@ struct dnbc_ctx {
   double *h_pinned = nullptr;   // small pinned bounce buffer
   size_t h_pinned_bytes = 0;
 
+  // tensor-core recursion (Npad >= 256): bf16 split tables, operand staging, row maxima
+  void *tc_tab = nullptr, *tc_x = nullptr;
+  float *tc_mrow = nullptr;
+  int64_t tc_mrow_cap = 0;
+
   // decode scratch
   double *E64 = nullptr;
   int64_t e64_points = 0;
@@ -161,6 +166,9 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out);
 void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np);
 bool fb2_supported(const dnbc_ctx *c);
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
+bool fb_tc_supported(const dnbc_ctx *c);
+void launch_tc_tables(dnbc_ctx *c);
+int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bool backward);
 void launch_fb_block(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 void launch_decode_block_f32(dnbc_ctx *c, int mode, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path,
                              double *score, uint8_t *tie, void *bp);

@@ -76,6 +76,7 @@ void launch_prepare_tables(dnbc_ctx *c) {
              c->t_pi, c->t_A, c->t_At, c->t_logpi, c->t_logA, c->t_cat, c->t_gs, c->t_gm, c->t_gc};
   c->launches++;
   k_prepare_tables<<<c->sm_count, 256, 0, c->stream>>>(a);
+  if (fb_tc_supported(c)) launch_tc_tables(c);   // bf16 split copies of A for the tensor-core recursion
 }
 
 // ---------------------------------------------------------------------------------

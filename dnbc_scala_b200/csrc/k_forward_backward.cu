@@ -251,6 +251,10 @@ static void launch_fb(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool back
   if (s1 <= s0) return;
   FamTimer ft(c, backward ? FAM_BACKWARD : FAM_FORWARD);
   if (fb2_supported(c)) return launch_fb2(c, s0, s1, p0, backward);   // register-resident A (k_fb2.cu)
+  if (fb_tc_supported(c)) {                                            // tcgen05 tensor cores (k_tc.cu)
+    launch_fb_tc(c, s0, s1, p0, c->h_off[s1] - c->h_off[s0], backward);
+    return;
+  }
   StatsLayout sl = stats_layout(c->dm);
   FbArgs a{c->dm, c->tables(), c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi};
   switch (c->dm.Npad) {

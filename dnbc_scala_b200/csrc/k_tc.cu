@@ -1,0 +1,432 @@
+// k_tc.cu -- K6: forward / backward recursions for large state spaces (Npad = 256 or 512) on
+// the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// No reference counterpart (the reference has no forward-backward); parity is
+// against the fp64 oracle (oracle/dnbc_oracle.c fb_one), same outputs as k_fb2.cu.
+//
+// For a batch of 128 sequences the step  alpha_t = b_t * (alpha_{t-1} A)  is a dense
+// [128 x N] x [N x N] contraction.  One CTA owns the batch for its whole length:
+//   * the accumulator D[128][N] fp32 lives in TMEM (N = 512 uses all 512 columns);
+//   * operands are bf16 SPLIT pairs (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)); the
+//     product is formed as hi*hi + hi*lo + lo*hi into the same fp32 accumulator (relative
+//     error ~2^-16 per term; a single bf16 pass would be ~2^-9, far outside the 1e-5 budget);
+//   * the transition matrix (K-major, [to][from] for the forward pass, [from][to] for the
+//     backward pass) streams from L2 in 64-wide K blocks through a 2-stage shared-memory ring
+//     in the canonical 128-byte-swizzled K-major layout (cp.async 16-byte chunks, XOR
+//     swizzle); one thread issues the tcgen05.mma's and commits to an mbarrier per stage;
+//   * the epilogue (8 warps, thread = (sequence row, half of the columns)) reads TMEM with
+//     tcgen05.ld, applies the emission, normalises the row, writes alpha / gamma / u to HBM and
+//     the next step's split operand to an L2-resident staging tile.
+// The step-to-step dependency (the epilogue of step t feeds the MMA of step t+1) serialises
+// MMA and epilogue within a CTA; 148 CTAs keep all SMs busy on independent batches.
+#include <cuda_bf16.h>
+
+#include "dnbc_internal.cuh"
+
+namespace {
+
+constexpr int TC_M = 128;          // sequences per CTA batch (UMMA M)
+constexpr int TC_NH = 256;         // UMMA N per instruction
+constexpr int TC_KB = 64;          // K block (one 128-byte swizzled row of bf16)
+constexpr int TC_THREADS = 256;
+constexpr int A_TILE = TC_M * TC_KB * 2;    // 16 KB
+constexpr int B_TILE = TC_NH * TC_KB * 2;   // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;   // hi + lo of both operands: 96 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+
+// rows x 64 bf16 tile: global row-major (ld elements per row) -> swizzled shared memory
+__device__ __forceinline__ void load_tile(uint32_t tile, const __nv_bfloat16 *g, int rows, int ld) {
+  for (int idx = threadIdx.x; idx < rows * 8; idx += TC_THREADS) {
+    const int r = idx >> 3, c = idx & 7;
+    cp_async16(tile + sw128(r, c), g + (size_t)r * ld + c * 8);
+  }
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 | LBO >> 4 at bit 16 | SBO >> 4 at bit 32 | version 1 at bit 46 | layout 2 at bit 61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 256
+__device__ __forceinline__ uint32_t umma_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NH >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      ::"r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31])),
+        "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// split 32 fp32 values into bf16 hi / lo and store both (64 B each) to the staging rows
+__device__ __forceinline__ void store_split(const float (&x)[32], __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ((uint4 *)hi)[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    ((uint4 *)lo)[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+  }
+}
+
+// 32 consecutive floats of a row: vector path when the row pitch keeps 16-byte alignment
+__device__ __forceinline__ void load32(const float *g, int j0, int N, bool vec, bool on, float fill, float (&v)[32]) {
+  if (on && vec) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = __ldg((const float4 *)(g + j0) + i);
+      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (on && j0 + i < N) ? g[j0 + i] : fill;
+  }
+}
+__device__ __forceinline__ void store32(float *g, int j0, int N, bool vec, const float (&v)[32]) {
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ((float4 *)(g + j0))[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (j0 + i < N) g[j0 + i] = v[i];
+  }
+}
+
+struct TcArgs {
+  int N, NP;                    // states, padded states (256 or 512)
+  const int64_t *off;
+  int64_t s0, s1, p0;
+  const float *E;               // [np][N]
+  const float *mrow;            // [np] max_j E
+  float *AL, *GA, *U, *cs;
+  double *stats;
+  int64_t st_pi;
+  const float *pi;              // [N]
+  const __nv_bfloat16 *Bh, *Bl; // [NP][NP] K-major operand B (forward: A^T, backward: A)
+  __nv_bfloat16 *Xh, *Xl;       // [grid][128][NP] staging of the next step's operand A
+};
+
+// D[128][NP] (TMEM) = X[128][NP] * B^T, X from the staging tile, B streamed from global
+__device__ void tc_gemm(const TcArgs &a, uint32_t smem_base, uint32_t bar0, uint32_t tmem, uint32_t (&uses)[2],
+                        const __nv_bfloat16 *xh, const __nv_bfloat16 *xl) {
+  const int NP = a.NP, nkb = NP / TC_KB, nnh = NP / TC_NH;
+  const uint32_t idesc = umma_idesc();
+  int it = 0;
+  for (int nh = 0; nh < nnh; ++nh) {
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int s = it & 1;
+      const uint32_t st = smem_base + s * STAGE_BYTES;
+      // the stage is free once the MMAs that read it two iterations ago have completed
+      if (uses[s] > 0) mbar_wait(bar0 + 8 * s, (uses[s] - 1) & 1);
+      load_tile(st, xh + kb * TC_KB, TC_M, NP);
+      load_tile(st + A_TILE, xl + kb * TC_KB, TC_M, NP);
+      load_tile(st + 2 * A_TILE, a.Bh + (size_t)nh * TC_NH * NP + kb * TC_KB, TC_NH, NP);
+      load_tile(st + 2 * A_TILE + B_TILE, a.Bl + (size_t)nh * TC_NH * NP + kb * TC_KB, TC_NH, NP);
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        const uint64_t dAh = umma_desc(st), dAl = umma_desc(st + A_TILE);
+        const uint64_t dBh = umma_desc(st + 2 * A_TILE), dBl = umma_desc(st + 2 * A_TILE + B_TILE);
+        const uint32_t d = tmem + nh * TC_NH;
+#pragma unroll
+        for (int k16 = 0; k16 < TC_KB / 16; ++k16) {
+          const uint64_t ko = (uint64_t)(k16 * 32 >> 4);     // 16 bf16 = 32 B further along K
+          umma_bf16(d, dAh + ko, dBh + ko, idesc, (kb | k16) ? 1u : 0u);
+          umma_bf16(d, dAh + ko, dBl + ko, idesc, 1u);
+          umma_bf16(d, dAl + ko, dBh + ko, idesc, 1u);
+        }
+        umma_commit(bar0 + 8 * s);
+      }
+      uses[s] += 1;
+    }
+  }
+  // all MMAs of this step have landed in TMEM
+  for (int s = 0; s < 2; ++s)
+    if (uses[s] > 0) mbar_wait(bar0 + 8 * s, (uses[s] - 1) & 1);
+  tc_fence_after();
+}
+
+template <int DIR>   // 0 = forward, 1 = backward
+__global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
+  extern __shared__ unsigned char smraw[];
+  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float rsum[TC_M][2];
+  __shared__ int sT[TC_M];
+  __shared__ int sTmax;
+  const int N = a.N, NP = a.NP;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int row = (w & 3) * 32 + lane, half = w >> 2;        // TMEM lane quadrant = warp % 4
+  const int ncol = NP / 2, col0 = half * ncol;               // this thread's column range
+  const bool vec = (N % 4) == 0 && N == NP;                  // rows are whole float4's and no padded columns
+  const uint32_t smem_base = (smem_u32(smraw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t trow = tmem + ((uint32_t)((w & 3) * 32) << 16);
+  uint32_t uses[2] = {0u, 0u};
+  __nv_bfloat16 *xh = a.Xh + (size_t)blockIdx.x * TC_M * NP, *xl = a.Xl + (size_t)blockIdx.x * TC_M * NP;
+  double ll = 0.0;
+
+  for (int64_t sb = a.s0 + (int64_t)blockIdx.x * TC_M; sb < a.s1; sb += (int64_t)gridDim.x * TC_M) {
+    const int64_t s = sb + row;
+    const int T = s < a.s1 ? (int)(a.off[s + 1] - a.off[s]) : 0;
+    const int64_t pt = s < a.s1 ? a.off[s] - a.p0 : 0;
+    if (tid == 0) sTmax = 0;
+    __syncthreads();
+    if (half == 0) { sT[row] = T; atomicMax(&sTmax, T); }
+    __syncthreads();
+    const int Tmax = sTmax;
+    for (int k = 0; k < Tmax; ++k) {
+      // forward walks t = k; backward walks t = T - 1 - k (rows aligned at their last step)
+      const int t = DIR == 0 ? k : T - 1 - k;
+      const bool live = DIR == 0 ? (k < T) : (t >= 0);
+      if (k > 0) tc_gemm(a, smem_base, bar0, tmem, uses, xh, xl);
+      const int64_t p = pt + (live ? t : 0);
+      const float *Erow = a.E + p * N;
+      const float mx = live ? a.mrow[p] : 0.f;
+      const float mxs = mx == -INFINITY ? 0.f : mx;
+      if (DIR == 0) {
+        // ---- v = d * exp(E - m); c = sum v; alpha = v / c ----
+        float sum = 0.f;
+        for (int ch = 0; ch < ncol / 32; ++ch) {
+          const int c0 = col0 + ch * 32;
+          float d[32], e[32];
+          if (k > 0) tmem_ld32(trow + c0, d);
+          else load32(a.pi, c0, N, false, true, 0.f, d);
+          load32(Erow, c0, N, vec, live, -INFINITY, e);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            d[i] *= ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E);
+            sum += d[i];
+          }
+          tmem_st32(trow + c0, d);
+        }
+        rsum[row][half] = sum;
+        __syncthreads();
+        const float c = rsum[row][0] + rsum[row][1];
+        const float inv = live ? 1.0f / c : 0.f;
+        for (int ch = 0; ch < ncol / 32; ++ch) {
+          const int c0 = col0 + ch * 32;
+          float d[32];
+          tmem_ld32(trow + c0, d);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d[i] *= inv;
+          if (live) store32(a.AL + p * N, c0, N, vec, d);
+          store_split(d, xh + (size_t)row * NP + c0, xl + (size_t)row * NP + c0);
+        }
+        if (live && half == 0) {
+          a.cs[p] = c;
+          ll += (double)logf(c) + (double)mxs;
+        }
+      } else {
+        // ---- beta_t in TMEM (1 on the last step); gamma = alpha * beta; next u = exp(E_t - m_t) beta / c_t ----
+        const float ic = live ? 1.0f / a.cs[p] : 0.f;
+        for (int ch = 0; ch < ncol / 32; ++ch) {
+          const int c0 = col0 + ch * 32;
+          float d[32], e[32], al[32];
+          if (k > 0) tmem_ld32(trow + c0, d);
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = 1.f;
+          }
+          load32(Erow, c0, N, vec, live, -INFINITY, e);
+          load32(a.AL + p * N, c0, N, vec, live, 0.f, al);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            al[i] *= d[i];                                                   // gamma
+            e[i] = (live && t > 0) ? ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E) * d[i] * ic : 0.f;   // next u
+          }
+          if (live) {
+            store32(a.GA + p * N, c0, N, vec, al);
+            if (t == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < N && al[i] != 0.f) atomicAdd(a.stats + a.st_pi + c0 + i, (double)al[i]);
+            }
+            if (t > 0) store32(a.U + (p - 1) * N, c0, N, vec, e);
+            if (k == 0) {                                                    // no transition out of the last step
+              float z[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) z[i] = 0.f;
+              store32(a.U + p * N, c0, N, vec, z);
+            }
+          }
+          store_split(e, xh + (size_t)row * NP + c0, xl + (size_t)row * NP + c0);
+        }
+      }
+      // TMEM reads done and the staging tile visible before the next step's MMAs / loads
+      tc_fence_before();
+      __threadfence();
+      __syncthreads();
+    }
+  }
+  if (DIR == 0 && half == 0 && ll != 0.0) atomicAdd(a.stats, ll);
+  tc_fence_before();
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// m[p] = max_j E[p][j]  (one warp per point)
+__global__ void k_rowmax(const float *__restrict__ E, int N, int64_t np, float *__restrict__ m) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; p < np; p += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    float v = -INFINITY;
+    for (int j = lane; j < N; j += 32) v = fmaxf(v, E[p * N + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) m[p] = v;
+  }
+}
+
+// bf16 split tables of the transition matrix: TA = [from][to] (backward), TAt = [to][from] (forward)
+__global__ void k_tc_tables(const double *__restrict__ A, int N, int NP, __nv_bfloat16 *Ah, __nv_bfloat16 *Al,
+                            __nv_bfloat16 *Ath, __nv_bfloat16 *Atl) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < (int64_t)NP * NP; q += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(q / NP), c = (int)(q % NP);
+    const float v = (r < N && c < N) ? (float)A[(int64_t)r * N + c] : 0.f;
+    const float vt = (r < N && c < N) ? (float)A[(int64_t)c * N + r] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v), ht = __float2bfloat16_rn(vt);
+    Ah[q] = h;
+    Al[q] = __float2bfloat16_rn(v - __bfloat162float(h));
+    Ath[q] = ht;
+    Atl[q] = __float2bfloat16_rn(vt - __bfloat162float(ht));
+  }
+}
+
+}  // namespace
+
+bool fb_tc_supported(const dnbc_ctx *c) {
+  static const bool off = getenv("DNBC_NO_TC") != nullptr;
+  return !off && (c->dm.Npad == 256 || c->dm.Npad == 512);
+}
+
+void launch_tc_tables(dnbc_ctx *c) {
+  const int NP = c->dm.Npad;
+  const size_t n = (size_t)NP * NP;
+  if (!c->tc_tab) {
+    if (cudaMalloc((void **)&c->tc_tab, 4 * n * sizeof(__nv_bfloat16)) != cudaSuccess) return;
+  }
+  __nv_bfloat16 *t = (__nv_bfloat16 *)c->tc_tab;
+  c->launches++;
+  k_tc_tables<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_A, c->dm.N, NP, t, t + n, t + 2 * n, t + 3 * n);
+}
+
+int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bool backward) {
+  const int NP = c->dm.Npad, N = c->dm.N;
+  const size_t n = (size_t)NP * NP;
+  const int64_t batches = (s1 - s0 + TC_M - 1) / TC_M;
+  int grid = (int)(batches < c->sm_count ? batches : c->sm_count);
+  if (grid < 1) grid = 1;
+  const size_t xbytes = (size_t)c->sm_count * TC_M * NP * sizeof(__nv_bfloat16);
+  if (!c->tc_x) {
+    if (cudaMalloc((void **)&c->tc_x, 2 * xbytes) != cudaSuccess) return DNBC_ENOMEM;
+  }
+  if (c->tc_mrow_cap < np) {
+    if (c->tc_mrow) cudaFree(c->tc_mrow);
+    c->tc_mrow = nullptr;
+    if (cudaMalloc((void **)&c->tc_mrow, (size_t)np * sizeof(float)) != cudaSuccess) return DNBC_ENOMEM;
+    c->tc_mrow_cap = np;
+  }
+  __nv_bfloat16 *t = (__nv_bfloat16 *)c->tc_tab;
+  StatsLayout sl = stats_layout(c->dm);
+  TcArgs a{N, NP, c->d_off, s0, s1, p0, c->E, c->tc_mrow, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi, c->t_pi,
+           backward ? t : t + 2 * n, backward ? t + n : t + 3 * n,
+           (__nv_bfloat16 *)c->tc_x, (__nv_bfloat16 *)((char *)c->tc_x + xbytes)};
+  const size_t smem = 2 * STAGE_BYTES + 1024;
+  if (!backward) {
+    c->launches++;
+    k_rowmax<<<c->sm_count * 8, 256, 0, c->stream>>>(c->E, N, np, c->tc_mrow);
+    cudaFuncSetAttribute(k_fb_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fb_tc<0><<<grid, TC_THREADS, smem, c->stream>>>(a);
+  } else {
+    cudaFuncSetAttribute(k_fb_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fb_tc<1><<<grid, TC_THREADS, smem, c->stream>>>(a);
+  }
+  return DNBC_OK;
+}

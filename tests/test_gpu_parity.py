@@ -339,6 +339,28 @@ def test_large_state_space_kernels(oracle):
     _paths_equal_except_ties(rp, rpath, rt, rtie, data.off)
 
 
+def test_tensor_core_recursion_n512(oracle):
+    """N = 512 exactly (BASELINE config 5 state count): the tcgen05 forward / backward kernels over
+    more than one 128-sequence batch with ragged lengths, against the fp64 oracle."""
+    m = random_model(oracle, 512, [6], [2], 84, transitions_per_state=64)
+    rng = np.random.default_rng(85)
+    lengths = [int(x) for x in rng.integers(1, 9, 150)] + [12, 1]
+    data = sample(oracle, m, lengths, 86)
+    q = perturb(oracle, m, 87)
+    want = oracle.estep(q, data)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        g = ctx.em_posteriors()
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    np.testing.assert_allclose(sg["pi"], sw["pi"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(sg["xi"], sw["xi"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(sg["gamma"], sw["gamma"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
+
+
 # ---------------------------------------------------------------------------------
 # generator, API surface, host mirror
 # ---------------------------------------------------------------------------------
