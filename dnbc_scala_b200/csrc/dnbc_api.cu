@@ -447,7 +447,9 @@ static int64_t chunk_budget_points(const dnbc_ctx *c, size_t bytes_per_point) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   size_t held = 0;  // scratch we already own can be reused
-  size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)12 << 30);
+  // up to a third of the free HBM: large chunks keep >= 148 batches of 128 sequences per launch at
+  // N = 512 (8 KB of scratch per point) and cut launch counts at N = 64
+  size_t budget = std::min<size_t>((free_b + held) / 3, (size_t)48 << 30);
   int64_t pts = (int64_t)(budget / std::max<size_t>(bytes_per_point, 1));
   pts = std::min<int64_t>(pts, (int64_t)1 << 30);   // kernels index chunk-relative points with 32 bits
   pts = std::max<int64_t>(pts, c->Tmax);

@@ -274,12 +274,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
       if (DIR == 0) {
         // ---- v = d * exp(E - m); c = sum v; alpha = v / c ----
         float sum = 0.f;
+        float e[32], en[32];
+        load32(Erow, col0, N, vec, live, -INFINITY, en);           // emission rows are fetched one chunk ahead
         for (int ch = 0; ch < ncol / 32; ++ch) {
           const int c0 = col0 + ch * 32;
-          float d[32], e[32];
+          float d[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) e[i] = en[i];
+          if (ch + 1 < ncol / 32) load32(Erow, c0 + 32, N, vec, live, -INFINITY, en);
           if (k > 0) tmem_ld32(trow + c0, d);
           else load32(a.pi, c0, N, false, true, 0.f, d);
-          load32(Erow, c0, N, vec, live, -INFINITY, e);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             d[i] *= ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E);
