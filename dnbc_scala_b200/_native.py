@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdnbc_b200.so")
+LIB_PATH = os.environ.get("DNBC_B200_LIB") or os.path.join(_HERE, "lib", "libdnbc_b200.so")   # override: A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECUDA, ENODEVICE, ESTATE, ENOMEM = range(6)

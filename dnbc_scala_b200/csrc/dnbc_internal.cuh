@@ -166,6 +166,8 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out);
 void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np);
 bool fb2_supported(const dnbc_ctx *c);
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
+bool xi_tc_supported(const dnbc_ctx *c);
+void launch_xi_tc(dnbc_ctx *c, int64_t np);
 bool fb_tc_supported(const dnbc_ctx *c);
 void launch_tc_tables(dnbc_ctx *c);
 int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bool backward);

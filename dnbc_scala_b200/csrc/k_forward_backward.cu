@@ -337,6 +337,10 @@ __global__ void __launch_bounds__(256) k_xi(int N, int Npad, const float *__rest
 void launch_xi(dnbc_ctx *c, int64_t np) {
   if (np <= 0) return;
   FamTimer ft(c, FAM_XI);
+  if (xi_tc_supported(c)) {                                  // N >= 64: tcgen05 GEMM (k_xi_tc.cu)
+    launch_xi_tc(c, np);
+    return;
+  }
   StatsLayout sl = stats_layout(c->dm);
   const int N = c->dm.N;
   if (N <= 16) {

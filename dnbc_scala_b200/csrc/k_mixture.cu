@@ -56,6 +56,11 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ u64 ex2_2(u64 a) {
   u64 d;
   asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tex2.approx.ftz.f32 lo, lo;\n\tex2.approx.ftz.f32 hi, hi;\n\t"
@@ -271,7 +276,10 @@ struct StatArgs {
   int LG, NW, window;
 };
 
-constexpr int SPB = 4;   // points whose posteriors are fetched together, one group ahead of their use
+#ifndef DNBC_STATS_SPB
+#define DNBC_STATS_SPB 4
+#endif
+constexpr int SPB = DNBC_STATS_SPB;   // points whose posteriors are fetched together, one group ahead of their use
 
 template <int KP>
 struct StatRegs {
@@ -315,16 +323,117 @@ __device__ __forceinline__ void stat_point(StatRegs<KP> &q, float x, float g) {
   }
 }
 
+// fast path, no exponent shift: 8 packed fp32 instructions + 2 MUFU per component pair
+// (z, z^2, c - z^2 | sum | r, S0, S1, S2) and no branch, so consecutive points interleave.
+// When the mixture sum underflows fp32 at a point that carries posterior mass (every component
+// > ~13 sigma away) the point contributes nothing here and the function returns true; the
+// caller then re-runs the flagged points of the block through the shifted stat_point above.
+#ifndef DNBC_STATS_FAST
+#define DNBC_STATS_FAST 1
+#endif
+template <int KP>
+__device__ __forceinline__ bool stat_point_fast(StatRegs<KP> &q, float x, float g) {
+  const float TINY = 1e-30f;
+  const u64 xx = pk(x, x);
+  u64 e[KP], z[KP], zz[KP];
+  u64 sum2;
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    z[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
+    zz[kp] = mul2(z[kp], z[kp]);
+    e[kp] = ex2_2(sub2(q.cc2[kp], zz[kp]));
+    sum2 = kp == 0 ? e[0] : add2(sum2, e[kp]);
+  }
+  const float sum = hsum(sum2);
+  const bool under = sum < TINY;
+  const float inv = under ? 0.f : g * rcp_approx(sum);
+  const u64 inv2 = pk(inv, inv);
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    const u64 rr = mul2(e[kp], inv2);
+    q.S0[kp] = add2(q.S0[kp], rr);
+    q.S1[kp] = fma2(rr, z[kp], q.S1[kp]);
+    q.S2[kp] = fma2(rr, zz[kp], q.S2[kp]);
+  }
+  return under && g != 0.f;
+}
+
+// The same fast path split in two stages so that stat_block can software-pipeline it: stage 1
+// (z, z^2, the 2K exponentials) of point p + 1 is issued together with stage 2 (normalise,
+// accumulate) of point p.  Without this the four warps of a scheduler fall into a convoy --
+// all in the MUFU phase, then all in the fp32 phase -- and the two pipes never overlap
+// (measured: 135 clk per warp-point = 72 MUFU + 64 fp32, profiles/r01_ncu_final.txt).
+#ifndef DNBC_STATS_PIPE
+#define DNBC_STATS_PIPE 1
+#endif
+// (holding z^2 of the pending point costs 8 registers and measured 7 % slower than recomputing it)
+#ifndef DNBC_STATS_HOLDZZ
+#define DNBC_STATS_HOLDZZ 0
+#endif
+#ifndef DNBC_STATS_NW
+#define DNBC_STATS_NW 8
+#endif
+template <int KP>
+struct StatPend {
+  u64 z[KP], e[KP];
+#if DNBC_STATS_HOLDZZ
+  u64 zz[KP];
+#endif
+  float g;
+};
+template <int KP>
+__device__ __forceinline__ void stat_stage1(const StatRegs<KP> &q, float x, float g, StatPend<KP> &n) {
+  const u64 xx = pk(x, x);
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    n.z[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
+    const u64 zz = mul2(n.z[kp], n.z[kp]);
+#if DNBC_STATS_HOLDZZ
+    n.zz[kp] = zz;
+#endif
+    n.e[kp] = ex2_2(sub2(q.cc2[kp], zz));
+  }
+  n.g = g;
+}
+template <int KP>
+__device__ __forceinline__ bool stat_stage2(StatRegs<KP> &q, const StatPend<KP> &p) {
+  const float TINY = 1e-30f;
+  u64 sum2 = p.e[0];
+#pragma unroll
+  for (int kp = 1; kp < KP; ++kp) sum2 = add2(sum2, p.e[kp]);
+  const float sum = hsum(sum2);
+  const bool under = sum < TINY;
+  const float inv = under ? 0.f : p.g * rcp_approx(sum);
+  const u64 inv2 = pk(inv, inv);
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    const u64 rr = mul2(p.e[kp], inv2);
+    q.S0[kp] = add2(q.S0[kp], rr);
+#if DNBC_STATS_HOLDZZ
+    q.S1[kp] = fma2(rr, p.z[kp], q.S1[kp]);
+    q.S2[kp] = fma2(rr, p.zz[kp], q.S2[kp]);
+#else
+    const u64 rz = mul2(rr, p.z[kp]);
+    q.S1[kp] = add2(q.S1[kp], rz);
+    q.S2[kp] = fma2(rz, p.z[kp], q.S2[kp]);
+#endif
+  }
+  return under && p.g != 0.f;
+}
+
 // 32 points: the warp-uniform role flags are template parameters so the inner loop carries no
 // per-point branches.  Posteriors are fetched SPB points ahead (gn) of the ones being consumed.
-// (A two-phase software pipeline across points was tried and was slower: it adds fp32 work to
-// a loop that is bound by register-file read bandwidth, see DESIGN.md.)
-template <int KP, bool HAS_C, bool HAS_D, bool GSUM>
+// FULL: all 32 points exist and the lane's state is real, so the posterior fetches carry no predicates.
+template <int KP, bool HAS_C, bool HAS_D, bool GSUM, bool FULL>
 __device__ __forceinline__ void stat_block(StatRegs<KP> &q, float &gs, float *bd, const float *gp, int gstep, float xreg,
-                                           int vreg, int LG, int PG, int lp, bool fast, int base, int pe, bool jon) {
+                                           int vreg, int LG, int PG, int lp, int base, int pe, bool jon) {
+  constexpr bool fast = FULL;
   float gn[SPB];
+  bool bad = false;
+  StatPend<KP> pend[2];
+  const float *gp0 = gp;
   auto fetch = [&](int blk) {
-    if (fast && blk + SPB <= LG) {
+    if (FULL) {                                              // (LG is a multiple of SPB when N >= SPB)
 #pragma unroll
       for (int i = 0; i < SPB; ++i) gn[i] = __ldg(gp + i * gstep);
     } else {
@@ -335,15 +444,30 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, float &gs, float *bd
     gp += SPB * gstep;
   };
   fetch(0);
+  if (HAS_C && DNBC_STATS_PIPE) stat_stage1<KP>(q, __shfl_sync(0xffffffffu, xreg, lp), gn[0], pend[0]);
   for (int blk = 0; blk < LG; blk += SPB) {                 // LG steps of PG points cover the 32 points
     float g[SPB];
 #pragma unroll
     for (int i = 0; i < SPB; ++i) g[i] = gn[i];
-    if (blk + SPB < LG) fetch(blk + SPB);
+    const bool more = blk + SPB < LG;
+    if (more) fetch(blk + SPB);
 #pragma unroll
     for (int i = 0; i < SPB; ++i) {
       const int qp = (blk + i) * PG + lp;                    // (steps past LG read lane qp & 31: g is 0 there)
-      if (HAS_C) stat_point<KP>(q, __shfl_sync(0xffffffffu, xreg, qp), g[i]);
+      if (HAS_C) {
+        if (DNBC_STATS_PIPE) {
+          // stage 1 of the next point rides with stage 2 of this one; two buffers alternate (no copies)
+          // (after the block's last point this evaluates one point too many and discards it:
+          // cheaper than a branch, which costs the compiler its register assignment)
+          const float xn = __shfl_sync(0xffffffffu, xreg, qp + PG);
+          stat_stage1<KP>(q, xn, i + 1 < SPB ? g[i + 1] : gn[0], pend[(i + 1) & 1]);
+          bad |= stat_stage2<KP>(q, pend[i & 1]);
+        } else {
+          const float x = __shfl_sync(0xffffffffu, xreg, qp);
+          if (DNBC_STATS_FAST) bad |= stat_point_fast<KP>(q, x, g[i]);
+          else stat_point<KP>(q, x, g[i]);
+        }
+      }
       if (HAS_D) {                                           // categorical histogram: bins[v][lane] += gamma
         const int v = __shfl_sync(0xffffffffu, vreg, qp);
         bd[v * 32] += g[i];
@@ -351,10 +475,25 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, float &gs, float *bd
       if (GSUM) gs += g[i];
     }
   }
+  if (HAS_C && (DNBC_STATS_FAST || DNBC_STATS_PIPE) && __any_sync(0xffffffffu, bad)) {
+    // rare: some point of this block sits where a state's whole mixture underflows fp32.  Redo the
+    // block through the shifted evaluation, each lane contributing only where its fast path gave up
+    // (the test below repeats stat_point_fast's: same inputs, same instructions, same outcome).
+#pragma unroll 1
+    for (int st = 0; st < LG; ++st) {
+      const bool on = fast || (base + st * PG + lp < pe && jon);
+      const float g = on ? __ldg(gp0 + (int64_t)st * gstep) : 0.f;
+      const float x = __shfl_sync(0xffffffffu, xreg, st * PG + lp);
+      StatRegs<KP> probe = q;
+      probe.S0[0] = 0ull;
+      const bool under = stat_point_fast<KP>(probe, x, g);
+      stat_point<KP>(q, x, under ? g : 0.f);
+    }
+  }
 }
 
 template <int KP>
-__global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
+__global__ void __launch_bounds__(DNBC_STATS_NW * 32, 16 / DNBC_STATS_NW > 3 ? 3 : 16 / DNBC_STATS_NW) k_stats_pk(StatArgs a) {
   extern __shared__ float bins[];                           // [warps of this CTA][Vmax+1][32]
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
   const int LG = a.LG, PG = 32 / LG, NW = a.NW;
@@ -410,8 +549,12 @@ __global__ void __launch_bounds__(256, 2) k_stats_pk(StatArgs a) {
       if (has_d) vnext = (int)__ldg(dcol + base + 32 + lane);
     }
     const float *gp = gcol + (int64_t)(base + lp) * N;      // posterior of this lane's state, step 0
-    const bool fast = full && jon;
-#define STAT_BLOCK(C_, D_, G_) stat_block<KP, C_, D_, G_>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, fast, base, pe, jon)
+    const bool fast = full && jon && LG >= SPB;
+#define STAT_BLOCK(C_, D_, G_)                                                                          \
+  do {                                                                                                 \
+    if (fast) stat_block<KP, C_, D_, G_, true>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, base, pe, jon);   \
+    else stat_block<KP, C_, D_, G_, false>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, base, pe, jon);       \
+  } while (0)
     if (has_c && has_d) { if (u == 0) STAT_BLOCK(true, true, true); else STAT_BLOCK(true, true, false); }
     else if (has_c) { if (u == 0) STAT_BLOCK(true, false, true); else STAT_BLOCK(true, false, false); }
     else if (has_d) { if (u == 0) STAT_BLOCK(false, true, true); else STAT_BLOCK(false, true, false); }
@@ -524,12 +667,14 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
   StatsLayout sl = stats_layout(d);
   int units = d.C > d.D ? d.C : d.D;
   if (units < 1) units = 1;
-  const int NW = units > 8 ? 8 : units;
+  const int NW = units > DNBC_STATS_NW ? DNBC_STATS_NW : units;
   const int gz = (units + NW - 1) / NW, gy = (d.Npad + 31) / 32;
   StatArgs a{d, c->tables(), c->data(), p0, (int)np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
              c->d_stats + sl.gamma, d.Npad < 32 ? d.Npad : 32, NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
-  int64_t gx = (int64_t)c->sm_count * 2 * (8 / NW > 4 ? 4 : 8 / NW) / ((int64_t)gy * gz);
+  // 16 warps per SM (128 registers each): CTAs of NW warps, e.g. 3 x 5 warps when 5 variables
+  const int per_sm = 16 / NW > 8 ? 8 : 16 / NW;
+  int64_t gx = (int64_t)c->sm_count * per_sm / ((int64_t)gy * gz);
   const int64_t maxgx = (np + 255) / 256;
   if (gx > maxgx) gx = maxgx;
   if (gx < 1) gx = 1;

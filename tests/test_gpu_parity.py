@@ -244,6 +244,33 @@ def test_estep_statistics_match_oracle(oracle, N, V, K, lengths):
     np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
 
 
+def test_estep_outliers_where_every_component_underflows_fp32(oracle):
+    """Points 15-25 sigma away from every component of every state: each mixture density is below
+    fp32's range but finite in the reference's doubles.  The emission and statistics sweeps take
+    their exponent-shifted paths there and must still match the fp64 oracle."""
+    m = random_model(oracle, 6, [5], [3, 2], 71)
+    m.var[0, :, :3] = 4.0
+    data = sample(oracle, m, [40] * 12 + [7, 1], 72)
+    rng = np.random.default_rng(73)
+    hit = rng.choice(data.P, size=37, replace=False)
+    data.cont[0, hit] = np.where(rng.random(37) < 0.5, 40.0, -40.0)
+    q = perturb(oracle, m, 74)
+    want = oracle.estep(q, data)
+    assert np.isfinite(want).all()
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    np.testing.assert_allclose(sg["gamma"], sw["gamma"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=1e-4, atol=1e-3, err_msg="gmm s0")
+    np.testing.assert_allclose(sg["gmm"][..., 1], sw["gmm"][..., 1], rtol=1e-4, atol=2e-2, err_msg="gmm s1")
+    np.testing.assert_allclose(sg["gmm"][..., 2], sw["gmm"][..., 2], rtol=1e-4, atol=0.5, err_msg="gmm s2")
+    # the outliers' responsibilities are in the statistics: sum_k s0 = gamma-sum per (variable, state)
+    np.testing.assert_allclose(sg["gmm"][0, :, :, 0].sum(-1), sg["gamma"], rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("N,V,K,S,T", [(10, [10] * 5, [3, 1, 4, 2, 3], 64, 200), (12, [4], [], 48, 200), (10, [], [3] * 5, 64, 200)])
 def test_em_iterations_match_oracle(oracle, N, V, K, S, T):
     """Learned pi / A / categorical / GMM parameters and the per-iteration log-likelihood within
