@@ -303,11 +303,26 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
             if (t >= 0 && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = 0.f;
         }
       }
+      // sum_i alpha^_t(i) beta^_t(i) is 1 in exact arithmetic; in fp32 the product of a thousand
+      // approximate normalisers drifts by ~3e-6, so beta^_t is rescaled to make it 1 at every step
+      float gsumq[SQ];
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        gsumq[q] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) gsumq[q] = fmaf(al[q][r], beta[q][r], gsumq[q]);
+      }
+#pragma unroll
+      for (int o = LG / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) gsumq[q] += __shfl_xor_sync(mask, gsumq[q], o, LG);
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         const int t = T[q] - 1 - k;
+        const float fix = gsumq[q] > 0.f ? rcp_approx(gsumq[q]) : 1.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+          beta[q][r] *= fix;
           const float g = al[q][r] * beta[q][r];
           if (t >= 0 && ir[r] < N) a.GA[row[q] + (int64_t)t * N + ir[r]] = g;
           if (t == 0) piacc[r] += (double)g;

@@ -425,10 +425,12 @@ __device__ __forceinline__ bool stat_stage2(StatRegs<KP> &q, const StatPend<KP> 
 // per-point branches.  Posteriors are fetched SPB points ahead (gn) of the ones being consumed.
 // FULL: all 32 points exist and the lane's state is real, so the posterior fetches carry no predicates.
 template <int KP, bool HAS_C, bool HAS_D, bool GSUM, bool FULL>
-__device__ __forceinline__ void stat_block(StatRegs<KP> &q, float &gs, float *bd, const float *gp, int gstep, float xreg,
+__device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *bd, const float *gp, int gstep, float xreg,
                                            int vreg, int LG, int PG, int lp, int base, int pe, bool jon) {
   constexpr bool fast = FULL;
   float gn[SPB];
+  float gsl = 0.f;   // gamma sum of this block; folded into fp64 per block (an fp32 running sum over a
+                     // 4096-point window reaches ~64 and would drop every posterior below 4e-6)
   bool bad = false;
   StatPend<KP> pend[2];
   const float *gp0 = gp;
@@ -472,9 +474,10 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, float &gs, float *bd
         const int v = __shfl_sync(0xffffffffu, vreg, qp);
         bd[v * 32] += g[i];
       }
-      if (GSUM) gs += g[i];
+      if (GSUM) gsl += g[i];
     }
   }
+  if (GSUM) gs += (double)gsl;
   if (HAS_C && (DNBC_STATS_FAST || DNBC_STATS_PIPE) && __any_sync(0xffffffffu, bad)) {
     // rare: some point of this block sits where a state's whole mixture underflows fp32.  Redo the
     // block through the shifted evaluation, each lane contributing only where its fast path gave up
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(DNBC_STATS_NW * 32, 16 / DNBC_STATS_NW > 3 ? 3
     q.s2[kp] = pk(v[0], v[1]); q.m2[kp] = pk(v[2], v[3]); q.cc2[kp] = pk(v[4], v[5]);
     q.S0[kp] = q.S1[kp] = q.S2[kp] = 0ull;
   }
-  float gs = 0.f;
+  double gs = 0.0;
   // contiguous slab of points per CTA column, aligned to 32 so x / symbol loads stay coalesced
   const int per = ((a.np + (int)gridDim.x - 1) / (int)gridDim.x + 31) / 32 * 32;
   const int pb = (int)blockIdx.x * per;
@@ -593,8 +596,8 @@ __global__ void __launch_bounds__(DNBC_STATS_NW * 32, 16 / DNBC_STATS_NW > 3 ? 3
         }
       }
       if (u == 0) {
-        if (jon && gs != 0.f) atomicAdd(a.gsum + j, (double)gs);
-        gs = 0.f;
+        if (jon && gs != 0.0) atomicAdd(a.gsum + j, gs);
+        gs = 0.0;
       }
       if (has_d) {
         for (int v = 0; v < Vmax; ++v) {

@@ -220,6 +220,8 @@ def test_decode_edge_cases(oracle):
     (12, [4], [], [200] * 16),                              # toy-robot shape (discrete only)
     (10, [], [3] * 5, [200] * 16),                          # config-3 shape
     (64, [10] * 4, [8] * 4, [100] * 6),                     # config-4 states / mixtures (fewer variables)
+    (70, [4], [2], [300] * 9 + [17, 1]),                    # tcgen05 xi: padded 128 x 128 tile, >1 window, ragged tail
+    (300, [3], [], [40] * 12 + [5]),                        # tcgen05 xi: two column tiles, the second partial
     (5, [3], [2], [1, 2, 3, 50, 7, 1]),                     # ragged, incl. length-1 sequences
 ])
 def test_estep_statistics_match_oracle(oracle, N, V, K, lengths):
@@ -386,6 +388,71 @@ def test_tensor_core_recursion_n512(oracle):
     np.testing.assert_allclose(sg["xi"], sw["xi"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(sg["gamma"], sw["gamma"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties (the oracle cannot run these)
+# ---------------------------------------------------------------------------------
+def _split(stats, N, D, C, V, K):
+    o, out = 1, {"ll": stats[0]}
+    for name, shape in (("pi", (N,)), ("xi", (N, N)), ("gamma", (N,)), ("cat", (D, N, V)), ("gmm", (C, N, K, 3))):
+        n = int(np.prod(shape))
+        out[name] = stats[o:o + n].reshape(shape)
+        o += n
+    return out
+
+
+@pytest.mark.parametrize("name,seqs", [("scaleout", 125_000), ("gmm100k", 100_000), ("largeN", 12_500)])
+def test_full_size_shards_keep_the_em_invariants(name, seqs):
+    """The per-GPU shard of BASELINE config 4 (125,000 x T=1000, N=64, 16+16 variables, K=8), config 3
+    at full size and config 5's 1/8 shard (N=512, tensor-core recursion): conservation laws of the
+    E-step, monotone log-likelihood over EM iterations, stochastic parameters after the M-step, and a
+    back-traced Viterbi decode that recovers the generating states."""
+    from dnbc_scala_b200 import workloads
+    wl = workloads.WORKLOADS[name]
+    truth = workloads.true_params(wl)
+    init = workloads.perturbed_params(wl, truth)
+    N, D, C, V, K = wl.N, wl.D, wl.C, wl.V, wl.K
+    P, S = seqs * wl.T, seqs
+    with nat.Context(N, [V] * D, [K] * C) as ctx:
+        ctx.set_params(truth["pi"], truth["A"], truth["B"], truth["w"], truth["mu"], truth["var"])
+        ctx.generate(seqs, wl.T, 777)
+        # decode with the generating parameters: the path is a valid state sequence and mostly the truth
+        path, score, _ = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+        _, _, _, labels = ctx.download(0, 64)
+        assert path.shape == (P,) and int(path.max()) < N and np.isfinite(score).all()
+        assert (path[:64 * wl.T] == labels).mean() > 0.25               # chance level is 1 / N <= 0.1
+        ctx.set_params(init["pi"], init["A"], init["B"], init["w"], init["mu"], init["var"])
+        ctx.em_estep()
+        st = _split(ctx.em_get_stats(), N, D, C, V, K)
+        assert np.isfinite(st["ll"]) and st["ll"] < 0
+        rel = 2e-6 if N <= 64 else 1e-5      # (the N >= 256 tensor-core recursion does not rescale beta per step)
+        assert abs(st["pi"].sum() - S) <= rel * S                       # one initial state per sequence
+        assert abs(st["gamma"].sum() - P) <= rel * P                    # one state per point
+        assert abs(st["xi"].sum() - (P - S)) <= rel * P                 # one transition per adjacent pair
+        for d in range(D):                                              # every point carries one symbol
+            np.testing.assert_allclose(st["cat"][d].sum(-1), st["gamma"], rtol=1e-5, atol=1e-3)
+        for c in range(C):                                              # responsibilities sum to the posterior
+            np.testing.assert_allclose(st["gmm"][c, :, :, 0].sum(-1), st["gamma"], rtol=1e-5, atol=1e-3)
+        # outgoing transition mass of state i = its posterior mass away from sequence ends (<= gamma)
+        assert (st["xi"].sum(1) <= st["gamma"] * (1 + 1e-5) + 1e-3).all()
+        ll = ctx.em_iterate(3)
+        assert abs(ll[0] - st["ll"]) <= 1e-6 * abs(st["ll"])            # same E-step, same likelihood
+        assert (np.diff(ll) >= -1e-7 * abs(ll[0])).all()                # EM never decreases it
+        p = ctx.get_params()
+        # (pi, B and w are normalised by the sequence count / gamma sums, SURVEY Appendix B: their rows
+        # sum to one up to the fp32 resolution of the posteriors; A rows are normalised by their own sum)
+        np.testing.assert_allclose(p["pi"].sum(), 1.0, rtol=3e-6)
+        np.testing.assert_allclose(p["A"].sum(1), 1.0, rtol=1e-9)
+        if D:
+            np.testing.assert_allclose(p["B"][:, :, :V].sum(-1), 1.0, rtol=3e-6)
+        if C:
+            np.testing.assert_allclose(p["w"][:, :, :K].sum(-1), 1.0, rtol=3e-6)
+            assert (p["var"][:, :, :K] > 0).all()
+            # learned from 10^6..10^8 points drawn from the truth: the means move towards it
+            want = np.sort(truth["mu"].reshape(C, N, -1)[:, :, :K], -1)
+            before = np.abs(np.sort(init["mu"].reshape(C, N, -1)[:, :, :K], -1) - want).mean()
+            assert np.abs(np.sort(p["mu"][:, :, :K], -1) - want).mean() < before
 
 
 # ---------------------------------------------------------------------------------
