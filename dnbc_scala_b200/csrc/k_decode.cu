@@ -217,6 +217,235 @@ __global__ void __launch_bounds__(256) k_decode(DecArgs<T> a) {
   }
 }
 
+// ---------------------------------------------------------------------------------
+// fast path: fp32 BACKTRACE mode, 4..64 (padded) states -- the Viterbi throughput metric.
+//
+// Same recursion, tie rule and outputs as k_decode<float, .., false> above, restructured around
+// what the generic kernel spends its time on (one shuffle per source state, a 4-way
+// compare/select per candidate, ln a_ij from global memory, a serial back-trace per warp):
+//   * column j of ln A lives in registers as packed pairs over the source index, delta_{t-1} is
+//     exchanged through a warp-private shared-memory line and read back as broadcast LDS.128;
+//   * pass 1 forms the N candidates of a destination with packed adds and reduces them with
+//     3-input max instructions to one maximum per block of 4 sources (1.5 issue slots per
+//     candidate instead of ~6), then the maximum over blocks;
+//   * pass 2 finds the arg-max exactly: the bit mask of blocks within the tie tolerance of the
+//     maximum has a single bit except at (flagged) ties, so the winner's block is ffs(mask) and
+//     only its 4 candidates are re-formed (ln A from a shared-memory copy, bit-identical adds)
+//     and compared for equality; at ties the whole warp takes the exact first-block search;
+//   * the back-trace is a separate kernel, one THREAD per sequence: the pointer chase is serial
+//     per sequence but 10^5 sequences chase concurrently (~1 ms instead of ~10^2 sequential walks
+//     per warp).
+// ---------------------------------------------------------------------------------
+typedef unsigned long long vu64;
+__device__ __forceinline__ vu64 vpk(float lo, float hi) {
+  vu64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void vadd2(vu64 a, vu64 b, float &lo, float &hi) {
+  vu64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+}
+
+constexpr int VW = 4;   // warps per CTA
+
+template <int LG, int R>
+__global__ void __launch_bounds__(VW * 32) k_viterbi2(DecArgs<float> a) {
+  constexpr int NP = LG * R, NB = NP / 4, PG = 32 / LG;
+  __shared__ __align__(16) float sv[VW][PG][NP];
+  __shared__ float sLA[NP * NP];                             // [from][to] copy of ln A for pass 2
+  const int N = a.dm.N;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
+  const unsigned mask = dgroup_mask<LG>();
+  bool act[R];
+  int jr[R];
+  vu64 LA[R][NP / 2];
+  for (int q = threadIdx.x; q < NP * NP; q += blockDim.x) {
+    const int i = q / NP, j = q % NP;
+    sLA[q] = (i < N && j < N && a.active[i] && a.active[j]) ? a.logA[(int64_t)i * a.lda + j] : -INFINITY;
+  }
+  __syncthreads();
+  int na = 0;
+  for (int j = 0; j < N; ++j) na += a.active[j] != 0;
+  const bool multi = na >= 2;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    jr[r] = lj + LG * r;
+    act[r] = jr[r] < N && a.active[jr[r]] != 0;
+#pragma unroll
+    for (int i = 0; i < NP; i += 2) LA[r][i / 2] = vpk(sLA[i * NP + jr[r]], sLA[(i + 1) * NP + jr[r]]);
+  }
+  float *svme = sv[w][gi];
+  const float4 *sv4 = (const float4 *)svme;
+  const int64_t ngroups = (int64_t)gridDim.x * VW * PG;
+  for (int64_t sw = a.s0 + ((int64_t)blockIdx.x * VW + w) * PG; sw < a.s1; sw += ngroups) {
+    const int64_t s = sw + gi;
+    const bool have = s < a.s1;                              // (a partly filled warp keeps all its lanes in step)
+    const int64_t b = have ? a.off[s] - a.p0 : 0, gb = have ? a.off[s] : 0;
+    const int Tn = have ? (int)(a.off[s + 1] - a.off[s]) : 0;
+    int Tmax = Tn;
+#pragma unroll
+    for (int o = 16; o >= LG; o >>= 1) { const int x = __shfl_xor_sync(0xffffffffu, Tmax, o); Tmax = x > Tmax ? x : Tmax; }
+    if (have && Tn <= 0 && lj == 0 && a.score) a.score[s] = 0.0;
+    float delta[R], en[R];
+    double shift = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      delta[r] = (act[r] && Tn > 0) ? a.E[b * N + jr[r]] + a.logpi[jr[r]] : -INFINITY;
+      en[r] = (act[r] && Tn > 1) ? a.E[(b + 1) * N + jr[r]] : -INFINITY;
+    }
+    for (int t = 1; t < Tmax; ++t) {
+      const bool live = t < Tn;
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < R; ++r) svme[jr[r]] = delta[r];
+      __syncwarp();
+      float e[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        e[r] = en[r];
+        en[r] = (act[r] && t + 1 < Tn) ? a.E[(b + t + 1) * N + jr[r]] : -INFINITY;
+      }
+      // ---- pass 1: block maxima of delta_{t-1}(i) + ln a_ij
+      float mb[R][NB];
+#pragma unroll
+      for (int bk = 0; bk < NB; ++bk) {
+        const float4 d = sv4[bk];
+        const vu64 d01 = vpk(d.x, d.y), d23 = vpk(d.z, d.w);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float c0, c1, c2, c3;
+          vadd2(d01, LA[r][2 * bk], c0, c1);
+          vadd2(d23, LA[r][2 * bk + 1], c2, c3);
+          mb[r][bk] = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+        }
+      }
+      float best[R], thr[R];
+      unsigned Q[R];
+      bool odd = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float m = mb[r][0];
+#pragma unroll
+        for (int bk = 1; bk < NB; ++bk) m = fmaxf(m, mb[r][bk]);
+        best[r] = m;
+        thr[r] = m - DNBC_TIE_TOL_F32;
+        unsigned qm = 0;
+#pragma unroll
+        for (int bk = 0; bk < NB; ++bk) qm |= (mb[r][bk] >= thr[r] ? 1u : 0u) << bk;
+        Q[r] = qm;
+        odd = odd || __popc(qm) != 1;
+      }
+      // ---- pass 2: the winner's block, then the winner
+      int bs[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) bs[r] = __ffs(Q[r]) - 1;
+      if (__any_sync(0xffffffffu, odd)) {                     // tie (or all -inf): exact first block holding the maximum
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int f = 0;
+#pragma unroll
+          for (int bk = NB - 1; bk >= 0; --bk) f = mb[r][bk] == best[r] ? bk : f;
+          bs[r] = f;
+        }
+      }
+      bool tie = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int bq = bs[r] < 0 ? 0 : bs[r];
+        const float4 d = sv4[bq];
+        const float *la = sLA + (bq * 4) * NP + jr[r];
+        const float c0 = d.x + la[0], c1 = d.y + la[NP], c2 = d.z + la[2 * NP], c3 = d.w + la[3 * NP];
+        int k = 3;
+        k = c2 == best[r] ? 2 : k;
+        k = c1 == best[r] ? 1 : k;
+        k = c0 == best[r] ? 0 : k;
+        const int near = (c0 >= thr[r]) + (c1 >= thr[r]) + (c2 >= thr[r]) + (c3 >= thr[r]);
+        const bool tr = __popc(Q[r]) != 1 || near >= 2 || !(best[r] - thr[r] > 0.f);
+        const int arg = bq * 4 + k;
+        if (act[r]) {
+          delta[r] = e[r] + best[r];
+          if (live) a.bp[(b + t) * N + jr[r]] = (uint16_t)arg;
+          tie = tie || (multi && tr);
+        }
+      }
+      tie = __any_sync(mask, tie);
+      // ---- renormalise (the shift is carried in fp64)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < R; ++r) mx = (act[r] && delta[r] > mx) ? delta[r] : mx;
+#pragma unroll
+      for (int o = LG / 2; o > 0; o >>= 1) { const float ov = __shfl_xor_sync(mask, mx, o, LG); mx = ov > mx ? ov : mx; }
+      if (live && mx > -INFINITY && mx < INFINITY) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) delta[r] -= mx;
+        shift += (double)mx;
+      }
+      if (a.tie && lj == 0 && live && tie) a.tie[gb + t] |= 2;
+      if (!live) {                                           // shorter sequence of a shared warp: freeze
+#pragma unroll
+        for (int r = 0; r < R; ++r) delta[r] = svme[jr[r]];
+      }
+    }
+    bool tiel;
+    const int last = group_first_argmax<float, LG, R>(delta, act, lj, mask, &tiel);
+    float bv = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < R; ++r) if (act[r] && jr[r] == last) bv = delta[r];
+#pragma unroll
+    for (int o = LG / 2; o > 0; o >>= 1) { const float ov = __shfl_xor_sync(mask, bv, o, LG); bv = ov > bv ? ov : bv; }
+    if (have && Tn > 0 && lj == 0) {
+      if (a.tie && tiel && multi) a.tie[gb + Tn - 1] |= 1;
+      if (a.score) a.score[s] = (double)bv + shift;
+      a.path[gb + Tn - 1] = (uint16_t)last;                   // k_backtrace starts from here
+    }
+  }
+}
+
+// one thread per sequence: walks the back-pointers from the last state k_viterbi2 left in path[]
+__global__ void k_backtrace(const int64_t *__restrict__ off, int64_t s0, int64_t s1, int64_t p0, int N,
+                            const uint16_t *__restrict__ bp, uint16_t *__restrict__ path) {
+  for (int64_t s = s0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < s1; s += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gb = off[s], b = gb - p0;
+    const int64_t Tn = off[s + 1] - gb;
+    if (Tn <= 0) continue;
+    int q = path[gb + Tn - 1];
+    for (int64_t t = Tn - 1; t >= 1; --t) {
+      q = __ldg(bp + (b + t) * N + q);
+      path[gb + t - 1] = (uint16_t)q;
+    }
+  }
+}
+
+template <int LG, int R>
+static void launch_viterbi2_t(dnbc_ctx *c, const DecArgs<float> &a) {
+  const int per_block = VW * (32 / LG);
+  const int64_t nseq = a.s1 - a.s0;
+  int64_t blocks = (nseq + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)c->sm_count * (LG * R > 32 ? 2 : 4);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_viterbi2<LG, R><<<(int)blocks, VW * 32, 0, c->stream>>>(a);
+  int64_t bb = (nseq + 127) / 128;
+  if (bb > c->sm_count * 16) bb = c->sm_count * 16;
+  c->launches++;
+  k_backtrace<<<(int)bb, 128, 0, c->stream>>>(a.off, a.s0, a.s1, a.p0, a.dm.N, a.bp, a.path);
+}
+
+static bool viterbi2(dnbc_ctx *c, int mode, const DecArgs<float> &a) {
+  static const bool off = getenv("DNBC_NO_VITERBI2") != nullptr;
+  if (off || mode != DNBC_DECODE_BACKTRACE) return false;
+  switch (c->dm.Npad) {
+    case 4: launch_viterbi2_t<4, 1>(c, a); return true;
+    case 8: launch_viterbi2_t<8, 1>(c, a); return true;
+    case 16: launch_viterbi2_t<16, 1>(c, a); return true;
+    case 32: launch_viterbi2_t<32, 1>(c, a); return true;
+    case 64: launch_viterbi2_t<32, 2>(c, a); return true;
+    default: return false;
+  }
+}
+
 template <typename T, int LG, int R>
 static void launch_decode_t(dnbc_ctx *c, int mode, const DecArgs<T> &a) {
   const int gpb = 256 / LG;
@@ -251,6 +480,7 @@ void launch_decode_f32(dnbc_ctx *c, int mode, int64_t s0, int64_t s1, int64_t p0
   if (c->dm.Npad >= 256) return launch_decode_block_f32(c, mode, s0, s1, p0, E, path, score, tie, bp);
   DecArgs<float> a{c->dm, c->d_off, s0, s1, p0, E, c->t_logpi, c->t_logA, c->dm.Npad, c->d_active, path, score, tie,
                    (uint16_t *)bp};
+  if (viterbi2(c, mode, a)) return;
   launch_decode_any<float>(c, mode, a);
 }
 
