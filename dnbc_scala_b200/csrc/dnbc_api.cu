@@ -433,6 +433,24 @@ static std::vector<Chunk> make_chunks(const dnbc_ctx *c, int64_t max_points) {
   return out;
 }
 
+// streamed upload: the first chunk's copy cannot overlap anything, so chunks start small and
+// double until they reach the scratch size (a kernel launch over few sequences still walks all
+// their timesteps, so many small chunks would leave the recursion kernels mostly idle)
+static std::vector<Chunk> make_chunks_progressive(const dnbc_ctx *c, int64_t first_points, int64_t max_points) {
+  std::vector<Chunk> out;
+  int64_t s = 0, want = std::min(first_points, max_points);
+  while (s < c->S) {
+    const int64_t p0 = c->h_off[s];
+    int64_t e = std::upper_bound(c->h_off.begin() + s + 1, c->h_off.end(), p0 + want) - c->h_off.begin() - 1;
+    if (e <= s) e = s + 1;
+    if (e > c->S) e = c->S;
+    out.push_back(Chunk{s, e, p0, c->h_off[e] - p0});
+    s = e;
+    want = std::min(want * 2, max_points);
+  }
+  return out;
+}
+
 // points the E-step scratch should hold: everything resident if it already fits, otherwise a
 // budget from the free memory (cudaMemGetInfo costs milliseconds, so it is only asked when the
 // scratch has to grow)
@@ -620,8 +638,7 @@ extern "C" int dnbc_em_estep_streamed(dnbc_ctx *c, int64_t n_seq, const int64_t 
   const int64_t maxp = em_scratch_target(c);
   rc = reserve_em_scratch(c, std::max(maxp, c->scratch_points));
   if (rc) return rc;
-  // finer chunks than the scratch allows shorten the un-overlapped first copy
-  const std::vector<Chunk> chunks = make_chunks(c, std::min<int64_t>(c->scratch_points, std::max<int64_t>(Tmax, (int64_t)4 << 20)));
+  const std::vector<Chunk> chunks = make_chunks_progressive(c, std::max<int64_t>(Tmax, (int64_t)2 << 20), c->scratch_points);
   if (!c->copy_stream) CU_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   while (c->chunk_events.size() < chunks.size() + 1) {
     cudaEvent_t e;

@@ -28,7 +28,6 @@ constexpr int XT = 256;     // threads per CTA
 constexpr int XKB = 64;     // points per K block = one 128-byte swizzled row of bf16
 constexpr int XWIN = 8;     // K blocks accumulated in TMEM before the window is folded into registers
 constexpr int XM = 128;     // UMMA M (from-states per tile; rows past N are zero)
-constexpr int XA_TILE = XM * XKB * 2;
 
 struct XiArgs {
   int N, Npad;
@@ -54,34 +53,54 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// rows [0, rows) of a K-major tile: row r = state col0 + r, K index = point p + k
-__device__ __forceinline__ void stage_tile(uint32_t tile_hi, uint32_t tile_lo, const float *__restrict__ src, int N, int col0,
-                                           int valid, int rows, int64_t p, int64_t pe) {
-  for (int q = threadIdx.x; q < rows * 8; q += XT) {
-    const int r = q % rows, c = q / rows;
-    const int64_t pp = p + c * 8;
-    float x[8];
-    if (r < valid && pp + 8 <= pe) {
-      const float *g = src + pp * N + col0 + r;
+// One staging item = 8 consecutive points of one state column = one 16-byte chunk of a K-major
+// tile row.  A thread's items are the same in every K block, so their coordinates are computed
+// once: `g` = element offset from the block's first point, `so` = swizzled byte offset in the tile.
+struct Item {
+  int g;
+  uint32_t so;
+  bool on;
+};
+__device__ __forceinline__ Item make_item(int q, int rows, int valid, int N, int col0) {
+  Item it;
+  const int r = q % rows, c = q / rows;
+  it.on = q < rows * 8 && r < valid;
+  it.g = c * 8 * N + col0 + r;
+  it.so = sw128(r, c);
+  return it;
+}
+__device__ __forceinline__ void load_item(const Item &it, const float *__restrict__ blk, int N, int64_t left, float (&x)[8]) {
+  if (it.on && left >= XKB) {                                // whole block inside the slab
+    const float *g = blk + it.g;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = __ldg(g + (int64_t)k * N);
-    } else {
+    for (int k = 0; k < 8; ++k) x[k] = __ldg(g + (int64_t)k * N);
+  } else {
+    const int k0 = (it.g / N);                               // first point of the chunk (col0 + r < N)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = (r < valid && pp + k < pe) ? __ldg(src + (pp + k) * N + col0 + r) : 0.f;
-    }
-    uint4 hi, lo;
-    split8(x, hi, lo);
-    const uint32_t o = sw128(r, c);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_hi + o), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + o), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+    for (int k = 0; k < 8; ++k) x[k] = (it.on && k0 + k < left) ? __ldg(blk + it.g + (int64_t)k * N) : 0.f;
   }
 }
+__device__ __forceinline__ void store_item(const Item &it, uint32_t tile_hi, uint32_t tile_lo, const float (&x)[8]) {
+  uint4 hi, lo;
+  split8(x, hi, lo);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_hi + it.so), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + it.so), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+}
 
-template <int NJ>   // UMMA N = to-states per tile (64, 128 or 256)
-__global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
-  constexpr int B_TILE = NJ * XKB * 2;
-  constexpr int STAGE = 2 * XA_TILE + 2 * B_TILE;
+// NJ = UMMA N = to-states per tile (64, 128 or 256); AM = rows of the A tile that exist in shared
+// memory.  The MMA is always M = 128: with AM = 64 (N <= 64) rows 64..127 of the operand are
+// whatever follows the tile in shared memory, which only produces accumulator rows 64..127 that
+// nobody reads -- the product is row-independent -- and halves the A tiles, so 3 CTAs fit an SM.
+template <int NJ, int AM>
+#ifndef DNBC_XI_OCC
+#define DNBC_XI_OCC 2
+#endif
+__global__ void __launch_bounds__(XT, NJ == 64 ? DNBC_XI_OCC : 1) k_xi_tc(XiArgs a) {
+  constexpr int A_TILE = AM * XKB * 2, B_TILE = NJ * XKB * 2;
+  constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   constexpr int NCOL = NJ / 2;                               // accumulator columns per thread
+  constexpr int IA = AM * 8 / XT, IB = NJ * 8 / XT;          // staging items per thread
+  constexpr bool PREFETCH = (IA + IB) * 8 <= 64;             // next block's rows ride in registers
   extern __shared__ unsigned char smraw[];
   __shared__ __align__(8) unsigned long long bars[2];
   __shared__ uint32_t tmem_slot;
@@ -90,8 +109,7 @@ __global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
   const int tiles = a.mtiles * a.ntiles;
   const int tile = blockIdx.x % tiles, slab = blockIdx.x / tiles;
   const int i0 = (tile % a.mtiles) * XM, j0 = (tile / a.mtiles) * 256;
-  const int vi = N - i0 < XM ? N - i0 : XM, vj = N - j0 < NJ ? N - j0 : NJ;
-  const int rows_i = (vi + 31) / 32 * 32, rows_j = (vj + 31) / 32 * 32 < NJ ? (vj + 31) / 32 * 32 : NJ;
+  const int vi = N - i0 < AM ? N - i0 : AM, vj = N - j0 < NJ ? N - j0 : NJ;
   const int64_t per = ((a.np + a.slabs - 1) / a.slabs + XKB - 1) / XKB * XKB;
   const int64_t pb = (int64_t)slab * per;
   const int64_t pe = pb + per < a.np ? pb + per : a.np;
@@ -107,8 +125,9 @@ __global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(NJ));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // rows that are never staged (states past N inside the 128 x NJ tile) stay zero
-  for (int o = tid * 16; o < 2 * STAGE; o += XT * 16)
+  // rows that are never staged (states past N inside the tile) stay zero; so does the pad after the
+  // last tile that an AM = 64 operand reads as its rows 64..127
+  for (int o = tid * 16; o < 2 * STAGE + (XM - AM) * 128; o += XT * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + o), "r"(0u) : "memory");
   tc_fence_before();
   __syncthreads();
@@ -117,10 +136,24 @@ __global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
   const int row = (w & 3) * 32 + lane, col0 = (w >> 2) * NCOL;     // TMEM lane quadrant = warp % 4
   const uint32_t trow = tmem + ((uint32_t)((w & 3) * 32) << 16) + col0;
   const uint32_t idesc = umma_idesc(XM, NJ);
+  const bool rows_live = (w & 3) * 32 < vi;                         // this warp's accumulator rows are real states
+
+  Item ia[IA], ib[IB];
+#pragma unroll
+  for (int n = 0; n < IA; ++n) ia[n] = make_item(tid + n * XT, AM, vi, N, i0);
+#pragma unroll
+  for (int n = 0; n < IB; ++n) ib[n] = make_item(tid + n * XT, NJ, vj, N, j0);
 
   float acc[NCOL];
 #pragma unroll
   for (int i = 0; i < NCOL; ++i) acc[i] = 0.f;
+  float xa[PREFETCH ? IA : 1][8], xb[PREFETCH ? IB : 1][8];
+  if (PREFETCH && pb < pe) {
+#pragma unroll
+    for (int n = 0; n < IA; ++n) load_item(ia[n], a.AL + pb * N, N, pe - pb, xa[n]);
+#pragma unroll
+    for (int n = 0; n < IB; ++n) load_item(ib[n], a.U + pb * N, N, pe - pb, xb[n]);
+  }
   uint32_t uses[2] = {0u, 0u};
   int inwin = 0, it = 0;
   for (int64_t p = pb; p < pe; p += XKB, ++it) {
@@ -128,14 +161,37 @@ __global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
     const uint32_t st = smem_base + s * STAGE;
     // the stage is free once the MMAs that read it two blocks ago have completed
     if (uses[s] > 0) mbar_wait(bar0 + 8 * s, (uses[s] - 1) & 1);
-    stage_tile(st, st + XA_TILE, a.AL, N, i0, vi, rows_i, p, pe);
-    stage_tile(st + 2 * XA_TILE, st + 2 * XA_TILE + B_TILE, a.U, N, j0, vj, rows_j, p, pe);
+    if (PREFETCH) {
+#pragma unroll
+      for (int n = 0; n < IA; ++n) store_item(ia[n], st, st + A_TILE, xa[n]);
+#pragma unroll
+      for (int n = 0; n < IB; ++n) store_item(ib[n], st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, xb[n]);
+      if (p + XKB < pe) {                                     // next block's loads fly during this block's MMAs
+#pragma unroll
+        for (int n = 0; n < IA; ++n) load_item(ia[n], a.AL + (p + XKB) * N, N, pe - p - XKB, xa[n]);
+#pragma unroll
+        for (int n = 0; n < IB; ++n) load_item(ib[n], a.U + (p + XKB) * N, N, pe - p - XKB, xb[n]);
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < IA; ++n) {
+        float x[8];
+        load_item(ia[n], a.AL + p * N, N, pe - p, x);
+        store_item(ia[n], st, st + A_TILE, x);
+      }
+#pragma unroll
+      for (int n = 0; n < IB; ++n) {
+        float x[8];
+        load_item(ib[n], a.U + p * N, N, pe - p, x);
+        store_item(ib[n], st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, x);
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t dAh = umma_desc(st), dAl = umma_desc(st + XA_TILE);
-      const uint64_t dBh = umma_desc(st + 2 * XA_TILE), dBl = umma_desc(st + 2 * XA_TILE + B_TILE);
+      const uint64_t dAh = umma_desc(st), dAl = umma_desc(st + A_TILE);
+      const uint64_t dBh = umma_desc(st + 2 * A_TILE), dBl = umma_desc(st + 2 * A_TILE + B_TILE);
 #pragma unroll
       for (int k16 = 0; k16 < XKB / 16; ++k16) {
         const uint64_t ko = (uint64_t)(k16 * 32 >> 4);       // 16 bf16 = 32 B further along K
@@ -150,12 +206,14 @@ __global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
       // fold the window into the register accumulators (fp32, round to nearest)
       mbar_wait(bar0 + 8 * s, (uses[s] - 1) & 1);
       tc_fence_after();
+      if (rows_live) {
 #pragma unroll
-      for (int ch = 0; ch < NCOL / 32; ++ch) {
-        float d[32];
-        tmem_ld32(trow + ch * 32, d);
+        for (int ch = 0; ch < NCOL / 32; ++ch) {
+          float d[32];
+          tmem_ld32(trow + ch * 32, d);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] += d[i];
+          for (int i = 0; i < 32; ++i) acc[ch * 32 + i] += d[i];
+        }
       }
       inwin = 0;
       tc_fence_before();
@@ -163,7 +221,7 @@ __global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
     }
   }
   const int i = i0 + row;
-  if (i < N) {
+  if (i < N && rows_live) {
 #pragma unroll
     for (int c = 0; c < NCOL; ++c) {
       const int j = j0 + col0 + c;
@@ -175,18 +233,18 @@ __global__ void __launch_bounds__(XT) k_xi_tc(XiArgs a) {
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(NJ));
 }
 
-template <int NJ>
+template <int NJ, int AM>
 void launch_t(dnbc_ctx *c, XiArgs a, int ctas_per_sm) {
-  constexpr int STAGE = 2 * XA_TILE + 2 * NJ * XKB * 2;
-  const size_t smem = 2 * STAGE + 1024;
+  constexpr int STAGE = 2 * AM * XKB * 2 + 2 * NJ * XKB * 2;
+  const size_t smem = 2 * STAGE + (XM - AM) * 128 + 1024;
   const int tiles = a.mtiles * a.ntiles;
   int64_t slabs = (int64_t)c->sm_count * ctas_per_sm / tiles;
   const int64_t maxslabs = (a.np + XKB * XWIN - 1) / (XKB * XWIN);
   if (slabs > maxslabs) slabs = maxslabs;
   if (slabs < 1) slabs = 1;
   a.slabs = (int)slabs;
-  cudaFuncSetAttribute(k_xi_tc<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_xi_tc<NJ><<<(unsigned)(slabs * tiles), XT, smem, c->stream>>>(a);
+  cudaFuncSetAttribute(k_xi_tc<NJ, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_xi_tc<NJ, AM><<<(unsigned)(slabs * tiles), XT, smem, c->stream>>>(a);
 }
 
 }  // namespace
@@ -200,7 +258,7 @@ void launch_xi_tc(dnbc_ctx *c, int64_t np) {
   const int N = c->dm.N;
   StatsLayout sl = stats_layout(c->dm);
   XiArgs a{N, c->dm.Npad, c->AL, c->U, np, c->t_A, c->d_stats + sl.xi, (N + XM - 1) / XM, (N + 255) / 256, 1};
-  if (N <= 64) launch_t<64>(c, a, 2);
-  else if (N <= 128) launch_t<128>(c, a, 1);
-  else launch_t<256>(c, a, 1);
+  if (N <= 64) launch_t<64, 64>(c, a, DNBC_XI_OCC);
+  else if (N <= 128) launch_t<128, 128>(c, a, 1);
+  else launch_t<256, 128>(c, a, 1);
 }
