@@ -160,7 +160,7 @@ extern "C" int dnbc_destroy(dnbc_ctx *c) {
                   c->t_gm,    c->t_gc,    c->t64_logpi, c->t64_logA, c->t64_logB, c->t64_u, c->t64_rs,  c->d_off,
                   c->d_disc,  c->d_cont,  c->d_cont64, c->d_labels, c->E,      c->AL,      c->GA,       c->U,
                   c->cs,      c->d_stats, c->E64,    c->d_bp,     c->d_path,   c->d_score, c->d_tie,    c->d_cnt,
-                  c->d_first_seq, c->d_assign, c->d_edge, c->d_edge_i, c->tc_tab, c->tc_x, c->tc_mrow};
+                  c->d_first_seq, c->d_assign, c->d_edge, c->d_edge_i, c->tc_tab, c->tc_x, c->tc_mrow, c->vt_logA};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);

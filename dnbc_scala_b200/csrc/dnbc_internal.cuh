@@ -90,6 +90,7 @@ struct dnbc_ctx {
   // tensor-core recursion (Npad >= 256): bf16 split tables, operand staging, row maxima
   void *tc_tab = nullptr, *tc_x = nullptr;
   float *tc_mrow = nullptr;
+  float *vt_logA = nullptr;          // [Npad][Npad] padded ln A for k_viterbi_tile.cu
   int64_t tc_mrow_cap = 0;
 
   // decode scratch
@@ -168,6 +169,10 @@ bool fb3_supported(const dnbc_ctx *c);
 void launch_fb3(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 bool fb2_supported(const dnbc_ctx *c);
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
+bool viterbi_tile_supported(const dnbc_ctx *c);
+int launch_viterbi_tile(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path, double *score,
+                        uint8_t *tie, uint16_t *bp);
+void launch_backtrace(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const uint16_t *bp, uint16_t *path);
 bool xi_tc_supported(const dnbc_ctx *c);
 void launch_xi_tc(dnbc_ctx *c, int64_t np);
 bool fb_tc_supported(const dnbc_ctx *c);

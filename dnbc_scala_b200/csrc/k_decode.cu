@@ -249,6 +249,7 @@ __device__ __forceinline__ void vadd2(vu64 a, vu64 b, float &lo, float &hi) {
 }
 
 constexpr int VW = 4;   // warps per CTA
+void launch_backtrace(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const uint16_t *bp, uint16_t *path);
 
 template <int LG, int R>
 __global__ void __launch_bounds__(VW * 32) k_viterbi2(DecArgs<float> a) {
@@ -427,10 +428,15 @@ static void launch_viterbi2_t(dnbc_ctx *c, const DecArgs<float> &a) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   k_viterbi2<LG, R><<<(int)blocks, VW * 32, 0, c->stream>>>(a);
-  int64_t bb = (nseq + 127) / 128;
+  launch_backtrace(c, a.s0, a.s1, a.p0, a.bp, a.path);
+}
+
+void launch_backtrace(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const uint16_t *bp, uint16_t *path) {
+  int64_t bb = (s1 - s0 + 127) / 128;
   if (bb > c->sm_count * 16) bb = c->sm_count * 16;
+  if (bb < 1) bb = 1;
   c->launches++;
-  k_backtrace<<<(int)bb, 128, 0, c->stream>>>(a.off, a.s0, a.s1, a.p0, a.dm.N, a.bp, a.path);
+  k_backtrace<<<(int)bb, 128, 0, c->stream>>>(c->d_off, s0, s1, p0, c->dm.N, bp, path);
 }
 
 static bool viterbi2(dnbc_ctx *c, int mode, const DecArgs<float> &a) {
@@ -477,6 +483,9 @@ void launch_decode_f32(dnbc_ctx *c, int mode, int64_t s0, int64_t s1, int64_t p0
                        double *score, uint8_t *tie, void *bp) {
   if (s1 <= s0) return;
   FamTimer ft(c, FAM_DECODE);
+  if (mode == DNBC_DECODE_BACKTRACE && viterbi_tile_supported(c) &&
+      launch_viterbi_tile(c, s0, s1, p0, E, path, score, tie, (uint16_t *)bp) == DNBC_OK)
+    return;                                                  // max-plus tiles (k_viterbi_tile.cu)
   if (c->dm.Npad >= 256) return launch_decode_block_f32(c, mode, s0, s1, p0, E, path, score, tie, bp);
   DecArgs<float> a{c->dm, c->d_off, s0, s1, p0, E, c->t_logpi, c->t_logA, c->dm.Npad, c->d_active, path, score, tie,
                    (uint16_t *)bp};

@@ -358,6 +358,7 @@ def test_large_state_space_kernels(oracle):
         ctx.em_estep()
         got = ctx.em_get_stats()
         path, score, tie = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F64)
+        p32, s32, t32 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)     # max-plus tiles (k_viterbi_tile.cu)
         rp, rs, rt = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
     sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
     assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
@@ -365,6 +366,8 @@ def test_large_state_space_kernels(oracle):
     np.testing.assert_allclose(sg["gamma"], sw["gamma"], rtol=1e-4, atol=1e-4)
     _paths_equal_except_ties(path, opath, tie, otie, data.off)
     np.testing.assert_allclose(score, oscore, rtol=1e-12)
+    _paths_equal_except_ties(p32, opath, t32, otie, data.off)
+    np.testing.assert_allclose(s32, oscore, rtol=1e-5)
     _paths_equal_except_ties(rp, rpath, rt, rtie, data.off)
 
 
@@ -382,6 +385,11 @@ def test_tensor_core_recursion_n512(oracle):
         ctx.em_estep()
         got = ctx.em_get_stats()
         g = ctx.em_posteriors()
+        p32, s32, t32 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)     # 5 batches of 32 ragged sequences
+    opath, oscore, otie = oracle.decode(q, data, oracle.DECODE_BACKTRACE)
+    _paths_equal_except_ties(p32, opath, t32, otie, data.off)
+    np.testing.assert_allclose(s32, oscore, rtol=1e-5)
+    assert (p32 == opath).mean() > 0.98
     sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
     assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
     np.testing.assert_allclose(sg["pi"], sw["pi"], rtol=1e-4, atol=1e-4)
