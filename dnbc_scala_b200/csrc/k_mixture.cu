@@ -331,6 +331,13 @@ __device__ __forceinline__ void stat_point(StatRegs<KP> &q, float x, float g) {
 #ifndef DNBC_STATS_FAST
 #define DNBC_STATS_FAST 1
 #endif
+// A state whose whole mixture underflows fp32 at a point almost always has a posterior far below
+// fp32 resolution there as well.  Only a posterior above this threshold sends the block through the
+// shifted re-evaluation; below it the point's contribution (< 1e-12 of one point's unit mass, against
+// sums of 10^2..10^8 and a 1e-5 parity budget) is dropped.
+#ifndef DNBC_STATS_GMIN
+#define DNBC_STATS_GMIN 1e-12f
+#endif
 template <int KP>
 __device__ __forceinline__ bool stat_point_fast(StatRegs<KP> &q, float x, float g) {
   const float TINY = 1e-30f;
@@ -355,7 +362,7 @@ __device__ __forceinline__ bool stat_point_fast(StatRegs<KP> &q, float x, float 
     q.S1[kp] = fma2(rr, z[kp], q.S1[kp]);
     q.S2[kp] = fma2(rr, zz[kp], q.S2[kp]);
   }
-  return under && g != 0.f;
+  return under && g > DNBC_STATS_GMIN;
 }
 
 // The same fast path split in two stages so that stat_block can software-pipeline it: stage 1
@@ -418,7 +425,7 @@ __device__ __forceinline__ bool stat_stage2(StatRegs<KP> &q, const StatPend<KP> 
     q.S2[kp] = fma2(rz, p.z[kp], q.S2[kp]);
 #endif
   }
-  return under && p.g != 0.f;
+  return under && p.g > DNBC_STATS_GMIN;
 }
 
 // 32 points: the warp-uniform role flags are template parameters so the inner loop carries no
