@@ -284,6 +284,14 @@ def run_b200(args, wl):
                 traffic = tr["bytes_per_point"] * pts_per_launch if tr else None
         except OSError:
             pass
+        # the dominant sweeps are bound by the SM's MUFU pipe (ex2 / lg2 / rcp), not by HBM: report that fraction too
+        mufu = None
+        if top in ("stats_gmm", "emission"):
+            sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+            per_clk_sm = wl.N * wl.C * (wl.K + 1) * pts_per_launch / (avg_ms * 1e-3 * sm_mhz * 1e6 * 148)
+            mufu = {"kernel": top, "achieved": per_clk_sm, "peak": 15.96, "unit": "MUFU lane-ops/clk/SM",
+                    "frac": per_clk_sm / 15.96, "ops_per_timestep": wl.N * wl.C * (wl.K + 1),
+                    "peak_source": "measured on this pool's B200 (tools/pipe_peaks.cu, profiles/r01_pipe_peaks.txt)"}
         step_ms = ms / args.steps
         fp32_tflops = wl.flops_per_timestep * seqs * wl.T / (step_ms * 1e-3) / 1e12
         line = {
@@ -295,7 +303,8 @@ def run_b200(args, wl):
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
                          "avg_launch_ms": avg_ms, "launches_in_timed_region": int(n_top),
                          "share_of_step": fam_ms[top] / max(1e-9, sum(fam_ms.values())),
-                         "note": "path is FP32/MUFU-pipe bound (SURVEY 8d): see fp32"},
+                         "note": "path is MUFU/FP32-pipe bound (SURVEY 8d), HBM fraction reported for form: see mufu and fp32"},
+            "mufu": mufu,
             "fp32": {"algorithmic_tflops_per_gpu": fp32_tflops, "nominal_peak_tflops": 74.4,
                      "frac_of_nominal": fp32_tflops / 74.4, "flops_per_timestep": wl.flops_per_timestep},
             "kernel_ms_per_step": {k: v / args.steps for k, v in fam_ms.items()},

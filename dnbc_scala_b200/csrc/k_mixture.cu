@@ -373,6 +373,10 @@ __device__ __forceinline__ bool stat_point_fast(StatRegs<KP> &q, float x, float 
 #ifndef DNBC_STATS_PIPE
 #define DNBC_STATS_PIPE 1
 #endif
+#ifndef DNBC_STATS_UNROLL
+#define DNBC_STATS_UNROLL 1
+#endif
+constexpr int STATS_UNROLL = DNBC_STATS_UNROLL;
 // (holding z^2 of the pending point costs 8 registers and measured 7 % slower than recomputing it)
 #ifndef DNBC_STATS_HOLDZZ
 #define DNBC_STATS_HOLDZZ 0
@@ -454,6 +458,7 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *b
   };
   fetch(0);
   if (HAS_C && DNBC_STATS_PIPE) stat_stage1<KP>(q, __shfl_sync(0xffffffffu, xreg, lp), gn[0], pend[0]);
+#pragma unroll STATS_UNROLL
   for (int blk = 0; blk < LG; blk += SPB) {                 // LG steps of PG points cover the 32 points
     float g[SPB];
 #pragma unroll
