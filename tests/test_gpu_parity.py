@@ -273,6 +273,35 @@ def test_estep_outliers_where_every_component_underflows_fp32(oracle):
     np.testing.assert_allclose(sg["gmm"][0, :, :, 0].sum(-1), sg["gamma"], rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("N", [2, 5, 17, 32, 33, 40, 63, 64, 65, 100, 128, 129, 200, 256])
+def test_every_state_count_dispatch_path_matches_oracle(oracle, N):
+    """The kernels are chosen by the (padded) state count: lane-group FP32 recursions (N <= 32 and odd
+    N <= 64), mma.sync recursion (even 33..64), generic lane groups (65..128), tcgen05 recursion
+    (129..512); tcgen05 xi from 64 up; fast Viterbi up to 64, max-plus tiles from 129.  One E-step and
+    one back-traced decode per size, ragged lengths, against the fp64 oracle."""
+    m = random_model(oracle, N, [4], [2], 300 + N, transitions_per_state=min(N, 12))
+    rng = np.random.default_rng(400 + N)
+    lengths = [int(x) for x in rng.integers(1, 40, 37)] + [1, 57]
+    data = sample(oracle, m, lengths, 500 + N)
+    q = perturb(oracle, m, 600 + N)
+    want = oracle.estep(q, data)
+    opath, oscore, otie = oracle.decode(q, data, oracle.DECODE_BACKTRACE)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        g = ctx.em_posteriors()
+        p32, s32, t32 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    for key in ("pi", "xi", "gamma", "cat"):
+        np.testing.assert_allclose(sg[key], sw[key], rtol=1e-4, atol=1e-4, err_msg=key)
+    np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=1e-4, atol=1e-3, err_msg="gmm s0")
+    np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
+    _paths_equal_except_ties(p32, opath, t32, otie, data.off)
+    np.testing.assert_allclose(s32, oscore, rtol=1e-5)
+
+
 @pytest.mark.parametrize("N,V,K,S,T", [(10, [10] * 5, [3, 1, 4, 2, 3], 64, 200), (12, [4], [], 48, 200), (10, [], [3] * 5, 64, 200)])
 def test_em_iterations_match_oracle(oracle, N, V, K, S, T):
     """Learned pi / A / categorical / GMM parameters and the per-iteration log-likelihood within
