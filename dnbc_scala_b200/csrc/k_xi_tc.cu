@@ -9,7 +9,7 @@
 //
 // The sum over points is a GEMM  xi = AL^T [N x P] * U [P x N]  with a huge reduction dimension
 // and a tiny output, so it is bound by reading AL and U once (2 * 4N bytes per point), not by
-// math.  One CTA owns an output tile of 128 x NJ states and a slab of points:
+// math.  One CTA owns an output tile of 128 x NJ states (NJ = 64 or 128) and a slab of points:
 //   * 256 threads read fp32 rows of AL / U (coalesced along the state index), split every value
 //     into bf16 hi + lo (x = hi + lo to ~2^-17) and write both TRANSPOSED into K-major,
 //     128-byte-swizzled operand tiles (one conflict-free 16-byte store per 8 points);
@@ -87,7 +87,7 @@ __device__ __forceinline__ void store_item(const Item &it, uint32_t tile_hi, uin
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + it.so), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
 }
 
-// NJ = UMMA N = to-states per tile (64, 128 or 256); AM = rows of the A tile that exist in shared
+// NJ = UMMA N = to-states per tile (64 or 128); AM = rows of the A tile that exist in shared
 // memory.  The MMA is always M = 128: with AM = 64 (N <= 64) rows 64..127 of the operand are
 // whatever follows the tile in shared memory, which only produces accumulator rows 64..127 that
 // nobody reads -- the product is row-independent -- and halves the A tiles, so 3 CTAs fit an SM.
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(XT, NJ == 64 ? DNBC_XI_OCC : 1) k_xi_tc(XiArgs
   const int N = a.N;
   const int tiles = a.mtiles * a.ntiles;
   const int tile = blockIdx.x % tiles, slab = blockIdx.x / tiles;
-  const int i0 = (tile % a.mtiles) * XM, j0 = (tile / a.mtiles) * 256;
+  const int i0 = (tile % a.mtiles) * XM, j0 = (tile / a.mtiles) * NJ;
   const int vi = N - i0 < AM ? N - i0 : AM, vj = N - j0 < NJ ? N - j0 : NJ;
   const int64_t per = ((a.np + a.slabs - 1) / a.slabs + XKB - 1) / XKB * XKB;
   const int64_t pb = (int64_t)slab * per;
@@ -257,8 +257,12 @@ bool xi_tc_supported(const dnbc_ctx *c) {
 void launch_xi_tc(dnbc_ctx *c, int64_t np) {
   const int N = c->dm.N;
   StatsLayout sl = stats_layout(c->dm);
-  XiArgs a{N, c->dm.Npad, c->AL, c->U, np, c->t_A, c->d_stats + sl.xi, (N + XM - 1) / XM, (N + 255) / 256, 1};
+  XiArgs a{N, c->dm.Npad, c->AL, c->U, np, c->t_A, c->d_stats + sl.xi, (N + XM - 1) / XM, 1, 1};
   if (N <= 64) launch_t<64, 64>(c, a, DNBC_XI_OCC);
-  else if (N <= 128) launch_t<128, 128>(c, a, 1);
-  else launch_t<256, 128>(c, a, 1);
+  else {
+    // 128 x 128 tiles: with 128 x 256 the 12 staging items per thread cannot be prefetched in
+    // registers and the load latency is exposed (measured 30 vs 11.7 ms per 4e6 points at N = 512)
+    a.ntiles = (N + 127) / 128;
+    launch_t<128, 128>(c, a, 1);
+  }
 }
