@@ -414,6 +414,7 @@ __global__ void k_backtrace(const int64_t *__restrict__ off, int64_t s0, int64_t
     int q = path[gb + Tn - 1];
     for (int64_t t = Tn - 1; t >= 1; --t) {
       q = __ldg(bp + (b + t) * N + q);
+      q = q < N ? q : N - 1;      // (only reachable on a sequence of probability zero, whose pointers are unset)
       path[gb + t - 1] = (uint16_t)q;
     }
   }
