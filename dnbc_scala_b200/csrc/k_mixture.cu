@@ -61,6 +61,13 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// c - a * b, packed: the negation is written on the halves so that ptxas folds it into the FFMA2
+__device__ __forceinline__ u64 fnma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("{\n\t.reg .f32 lo, hi;\n\t.reg .b64 n;\n\tmov.b64 {lo, hi}, %1;\n\tneg.f32 lo, lo;\n\tneg.f32 hi, hi;\n\t"
+      "mov.b64 n, {lo, hi};\n\tfma.rn.f32x2 %0, n, %2, %3;\n\t}" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ u64 ex2_2(u64 a) {
   u64 d;
   asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tex2.approx.ftz.f32 lo, lo;\n\tex2.approx.ftz.f32 hi, hi;\n\t"
@@ -398,11 +405,13 @@ __device__ __forceinline__ void stat_stage1(const StatRegs<KP> &q, float x, floa
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     n.z[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
-    const u64 zz = mul2(n.z[kp], n.z[kp]);
 #if DNBC_STATS_HOLDZZ
+    const u64 zz = mul2(n.z[kp], n.z[kp]);
     n.zz[kp] = zz;
-#endif
     n.e[kp] = ex2_2(sub2(q.cc2[kp], zz));
+#else
+    n.e[kp] = ex2_2(fnma2(n.z[kp], n.z[kp], q.cc2[kp]));
+#endif
   }
   n.g = g;
 }
@@ -508,7 +517,10 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *b
 }
 
 template <int KP>
-__global__ void __launch_bounds__(DNBC_STATS_NW * 32, 16 / DNBC_STATS_NW > 3 ? 3 : 16 / DNBC_STATS_NW) k_stats_pk(StatArgs a) {
+#ifndef DNBC_STATS_OCC
+#define DNBC_STATS_OCC (16 / DNBC_STATS_NW > 3 ? 3 : 16 / DNBC_STATS_NW)
+#endif
+__global__ void __launch_bounds__(DNBC_STATS_NW * 32, DNBC_STATS_OCC) k_stats_pk(StatArgs a) {
   extern __shared__ float bins[];                           // [warps of this CTA][Vmax+1][32]
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
   const int LG = a.LG, PG = 32 / LG, NW = a.NW;
@@ -688,7 +700,11 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
              c->d_stats + sl.gamma, d.Npad < 32 ? d.Npad : 32, NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
   // 16 warps per SM (128 registers each): CTAs of NW warps, e.g. 3 x 5 warps when 5 variables
+#ifdef DNBC_STATS_PER_SM
+  const int per_sm = DNBC_STATS_PER_SM;
+#else
   const int per_sm = 16 / NW > 8 ? 8 : 16 / NW;
+#endif
   int64_t gx = (int64_t)c->sm_count * per_sm / ((int64_t)gy * gz);
   const int64_t maxgx = (np + 255) / 256;
   if (gx > maxgx) gx = maxgx;
