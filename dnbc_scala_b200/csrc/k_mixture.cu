@@ -106,13 +106,8 @@ template <int KP>
 __device__ __forceinline__ void emit_var(const float4 *ps, const float2 *pc, const float (&x)[EPU], float (&acc)[EPU]) {
   const u64 neg1 = pk(-1.f, -1.f);
   u64 xx[EPU], sum2[EPU];
-  float mx[EPU];
 #pragma unroll
-  for (int i = 0; i < EPU; ++i) {
-    xx[i] = pk(x[i], x[i]);
-    sum2[i] = 0ull;
-    mx[i] = -INFINITY;
-  }
+  for (int i = 0; i < EPU; ++i) xx[i] = pk(x[i], x[i]);
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     const float4 sm4 = ps[kp * 32];
@@ -121,29 +116,40 @@ __device__ __forceinline__ void emit_var(const float4 *ps, const float2 *pc, con
 #pragma unroll
     for (int i = 0; i < EPU; ++i) {
       const u64 z2 = fma2(xx[i], s2, m2);
-      const u64 a2 = fma2(mul2(z2, z2), neg1, cc2);
-      mx[i] = max3lohi(mx[i], a2);
-      sum2[i] = add2(sum2[i], ex2_2(a2));
+      const u64 e2 = ex2_2(fnma2(z2, z2, cc2));
+      sum2[i] = kp == 0 ? e2 : add2(sum2[i], e2);
     }
   }
 #pragma unroll
   for (int i = 0; i < EPU; ++i) {
     const float sum = hsum(sum2[i]);
     float L = lg2_approx(sum);                       // lg2(0) = -inf: no component has mass
-    if (sum < 1e-30f && mx[i] != -INFINITY) {
-      // every component underflowed fp32 (> ~13 sigma away): redo shifted by the largest
-      // exponent, so the result stays finite where the reference's fp64 sum is finite
-      u64 s = 0ull;
-      const u64 nm = pk(-mx[i], -mx[i]);
+    if (sum < 1e-30f) {
+      // every component underflowed fp32 (> ~13 sigma away), or none has mass: redo with the
+      // exponents shifted by their maximum, so the result stays finite where the reference's fp64
+      // sum is finite.  Rare per (point, state, variable); the maximum is only computed here.
+      float mx = -INFINITY;
 #pragma unroll 1
       for (int kp = 0; kp < KP; ++kp) {
         const float4 sm4 = ps[kp * 32];
         const float2 cc = pc[kp * 32];
         const u64 z2 = fma2(xx[i], pk(sm4.x, sm4.y), pk(sm4.z, sm4.w));
-        const u64 a2 = fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y));
-        s = add2(s, ex2_2(add2(a2, nm)));
+        mx = max3lohi(mx, fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y)));
       }
-      L = mx[i] + lg2_approx(hsum(s));
+      if (mx != -INFINITY) {
+        u64 s = 0ull;
+        const u64 nm = pk(-mx, -mx);
+#pragma unroll 1
+        for (int kp = 0; kp < KP; ++kp) {
+          const float4 sm4 = ps[kp * 32];
+          const float2 cc = pc[kp * 32];
+          const u64 z2 = fma2(xx[i], pk(sm4.x, sm4.y), pk(sm4.z, sm4.w));
+          s = add2(s, ex2_2(add2(fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y)), nm)));
+        }
+        L = mx + lg2_approx(hsum(s));
+      } else {
+        L = -INFINITY;
+      }
     }
     acc[i] += L;
   }
@@ -173,7 +179,8 @@ __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
       const int64_t o = ((int64_t)c * Kmax + (k < Kmax ? k : 0)) * Npad + (j < Npad ? j : 0);
       v[h] = on ? a.tb.gs[o] : 0.f;
       v[2 + h] = on ? a.tb.gm[o] : 0.f;
-      v[4 + h] = on ? a.tb.gc[o] : -INFINITY;
+      // (padded lanes get unit-mass components so they never look like an underflowed mixture)
+      v[4 + h] = on ? a.tb.gc[o] : (j < N ? -INFINITY : 0.f);
     }
     sm_sm[t] = make_float4(v[0], v[1], v[2], v[3]);
     sm_cc[t] = make_float2(v[4], v[5]);
