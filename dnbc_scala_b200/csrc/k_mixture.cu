@@ -200,77 +200,105 @@ __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
   const int64_t P = a.dv.P;
   const bool vec = a.vec && PG == 1;
   const int cstride = KP * 32;
+  const int tstride = (Vmax + 1) * 32;
   for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * wpb) {
     const int pb = g * group;
     const bool full = pb + group <= a.np;
-    int po[EPU];                                            // this lane's points (chunk-relative)
-#pragma unroll
-    for (int i = 0; i < EPU; ++i) po[i] = pb + i * PG + lp;
     float acc[EPU];
 #pragma unroll
     for (int i = 0; i < EPU; ++i) acc[i] = 0.f;
-    // observations of variable c for this lane's EPU points; fetched one variable ahead
-    auto load_x = [&](int c, float (&x)[EPU]) {
-      const float *col = cont0 + (int64_t)c * P;
-      if (vec && full) {
-        const float4 v = __ldg((const float4 *)(col + pb));
-        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < EPU; ++i) x[i] = po[i] < a.np ? __ldg(col + po[i]) : 0.f;
-      }
-    };
-    // symbols of discrete variable d for this lane's EPU points, packed one byte per point
-    auto load_v = [&](int d) -> uint32_t {
-      const uint8_t *col = disc0 + (int64_t)d * P;
-      if (vec && full) return __ldg((const uint32_t *)(col + pb));
-      uint32_t w4 = 0;
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) w4 |= (po[i] < a.np ? (uint32_t)__ldg(col + po[i]) : (uint32_t)Vmax) << (8 * i);
-      return w4;
-    };
-    auto add_cat = [&](const float *tab, uint32_t w4) {
+    const float4 *ps = sm_sm + lane;
+    const float2 *pc = sm_cc + lane;
+    const float *tab = sm_cat + lane;
+    auto add_cat = [&](uint32_t w4) {                        // one symbol per byte; ids >= V mean "never seen"
 #pragma unroll
       for (int i = 0; i < EPU; ++i) {
-        const int v = (int)((w4 >> (8 * i)) & 0xffu);
+        const int v = (int)__byte_perm(w4, 0u, 0x4440 + i);
         acc[i] += tab[(v < Vmax ? v : Vmax) * 32];
       }
+      tab += tstride;
     };
     // variable c + 1's observations (and discrete variable c + 1's symbols) are fetched while
     // variable c is evaluated, so no load latency is exposed
     float xc[EPU], xn[EPU];
     uint32_t vc = 0, vn = 0;
+    if (vec && full) {
+      // fast path: 4 consecutive points per lane, one 16-byte and one 4-byte load per variable, the
+      // plane pointers advanced by P per variable (no per-variable address arithmetic or predicates)
+      const float *xp = cont0 + pb;
+      const uint8_t *vp = disc0 + pb;
+      auto ldx = [&](float (&x)[EPU]) {
+        const float4 v = __ldg((const float4 *)xp);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+      };
+      if (C > 0) ldx(xc);
+      if (D > 0) vc = __ldg((const uint32_t *)vp);
+      for (int c = 0; c < C; ++c) {
+        xp += P;
+        vp += P;
+        if (c + 1 < C) ldx(xn);
+        if (c + 1 < D) vn = __ldg((const uint32_t *)vp);
+        emit_var<KP>(ps, pc, xc, acc);
+        ps += cstride;
+        pc += cstride;
+        if (c < D) add_cat(vc);
+#pragma unroll
+        for (int i = 0; i < EPU; ++i) xc[i] = xn[i];
+        vc = vn;
+      }
+      for (int d = C; d < D; ++d) {                          // more discrete than continuous variables
+        vp += P;                                             // (vp pointed at variable d's plane)
+        if (d + 1 < D) vn = __ldg((const uint32_t *)vp);
+        add_cat(vc);
+        vc = vn;
+      }
+      if (j < N) {
+        float *dst = a.E + (int64_t)pb * N + j;
+#pragma unroll
+        for (int i = 0; i < EPU; ++i) dst[(int64_t)i * N] = acc[i] * (float)DNBC_LN2;
+      }
+      continue;
+    }
+    int po[EPU];                                            // this lane's points (chunk-relative)
+#pragma unroll
+    for (int i = 0; i < EPU; ++i) po[i] = pb + i * PG + lp;
+    auto load_x = [&](int c, float (&x)[EPU]) {
+      const float *col = cont0 + (int64_t)c * P;
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) x[i] = po[i] < a.np ? __ldg(col + po[i]) : 0.f;
+    };
+    auto load_v = [&](int d) -> uint32_t {
+      const uint8_t *col = disc0 + (int64_t)d * P;
+      uint32_t w4 = 0;
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) w4 |= (po[i] < a.np ? (uint32_t)__ldg(col + po[i]) : (uint32_t)Vmax) << (8 * i);
+      return w4;
+    };
     if (C > 0) load_x(0, xc);
     if (D > 0) vc = load_v(0);
-    const float4 *ps = sm_sm + lane;
-    const float2 *pc = sm_cc + lane;
-    const float *tab = sm_cat + lane;
-    const int tstride = (Vmax + 1) * 32;
+#pragma unroll 1
     for (int c = 0; c < C; ++c) {
       if (c + 1 < C) load_x(c + 1, xn);
       if (c + 1 < D) vn = load_v(c + 1);
       emit_var<KP>(ps, pc, xc, acc);
       ps += cstride;
       pc += cstride;
-      if (c < D) {
-        add_cat(tab, vc);
-        tab += tstride;
-      }
+      if (c < D) add_cat(vc);
 #pragma unroll
       for (int i = 0; i < EPU; ++i) xc[i] = xn[i];
       vc = vn;
     }
+#pragma unroll 1
     for (int d = C; d < D; ++d) {                           // more discrete than continuous variables
       if (d + 1 < D) vn = load_v(d + 1);
-      add_cat(tab, vc);
-      tab += tstride;
+      add_cat(vc);
       vc = vn;
     }
     if (j < N) {
       float *dst = a.E + (int64_t)pb * N + j;
 #pragma unroll
       for (int i = 0; i < EPU; ++i)
-        if (full || po[i] < a.np) dst[(int64_t)(i * PG + lp) * N] = acc[i] * (float)DNBC_LN2;
+        if (po[i] < a.np) dst[(int64_t)(i * PG + lp) * N] = acc[i] * (float)DNBC_LN2;
     }
   }
 }
