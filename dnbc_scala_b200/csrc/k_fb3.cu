@@ -19,7 +19,8 @@
 //     conflict-free; forward uses [to][from], backward [from][to];
 //   * emission / alpha rows are read and written straight in the accumulator layout: a lane owns
 //     columns 8 nt + 2 q, + 1 of rows g and g + 8, i.e. one 8-byte access per (row, tile), whole
-//     32-byte sectors per quad; next step's rows are prefetched during this step's MMAs;
+//     32-byte sectors per quad; a step's rows are requested at its top and first used after its
+//     96 MMAs (prefetching a step ahead costs 32 registers, i.e. a CTA per SM: measured 17 % slower);
 //   * the row normaliser is a 2-step quad shuffle.
 // The step is bound by HBM (forward: read E, write alpha^; backward: read E, alpha^, write gamma,
 // u = 4 N floats per point) instead of by the FP32 pipe as in k_fb2.cu.
@@ -154,7 +155,13 @@ __device__ __forceinline__ RowInfo rows_of(const Fb3Args &a, int64_t sb, int g, 
 }
 
 // ---- forward: alpha^_t(j) = b~_t(j) sum_i alpha^_{t-1}(i) a_ij / c_t ;  LL += ln c_t + m_t
-__global__ void __launch_bounds__(FB3_WARPS * 32, 3) k_forward3(Fb3Args a) {
+#ifndef DNBC_FB3_FWD_PREFETCH
+#define DNBC_FB3_FWD_PREFETCH 0
+#endif
+#ifndef DNBC_FB3_FWD_OCC
+#define DNBC_FB3_FWD_OCC 3
+#endif
+__global__ void __launch_bounds__(FB3_WARPS * 32, DNBC_FB3_FWD_OCC) k_forward3(Fb3Args a) {
   __shared__ __align__(1024) unsigned char sB[2][NP * 128];
   const int N = a.N;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
@@ -174,17 +181,24 @@ __global__ void __launch_bounds__(FB3_WARPS * 32, 3) k_forward3(Fb3Args a) {
     const RowInfo ri = rows_of(a, sb, g, Tmax);
     const float *Er[2] = {a.E + ri.pt[0] * N, a.E + ri.pt[1] * N};
     float *Ar[2] = {a.AL + ri.pt[0] * N, a.AL + ri.pt[1] * N};
+#if DNBC_FB3_FWD_PREFETCH
     float en[2][NT][2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) load_row(Er[h], N, q, ri.T[h] > 0, -INFINITY, en[h]);
+#endif
     uint32_t xh[KT][4], xl[KT][4];
     for (int t = 0; t < Tmax; ++t) {
       float e[2][NT][2], acc[NT][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+#if DNBC_FB3_FWD_PREFETCH
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { e[h][nt][0] = en[h][nt][0]; e[h][nt][1] = en[h][nt][1]; }
         load_row(Er[h] + (int64_t)(t + 1) * N, N, q, t + 1 < ri.T[h], -INFINITY, en[h]);
+#else
+        // this step's emission row is requested here and first used after the step's 96 MMAs
+        load_row(Er[h] + (int64_t)t * N, N, q, t < ri.T[h], -INFINITY, e[h]);
+#endif
       }
       if (t == 0) {
 #pragma unroll
@@ -263,10 +277,9 @@ __global__ void __launch_bounds__(FB3_WARPS * 32, DNBC_FB3_BWD_OCC) k_backward3(
     const RowInfo ri = rows_of(a, sb, g, Tmax);
     const int64_t r0[2] = {ri.pt[0] * N, ri.pt[1] * N};
     // rows are aligned at their LAST step: iteration k handles t = T - 1 - k
-    float aln[2][NT][2], en[2][NT][2], csn[2];
+    float en[2][NT][2], csn[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      load_row(a.AL + r0[h] + (int64_t)(ri.T[h] - 1) * N, N, q, ri.T[h] > 0, 0.f, aln[h]);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) en[h][nt][0] = en[h][nt][1] = -INFINITY;
       csn[h] = 1.f;
@@ -280,12 +293,10 @@ __global__ void __launch_bounds__(FB3_WARPS * 32, DNBC_FB3_BWD_OCC) k_backward3(
         t[h] = ri.T[h] - 1 - k;
         cn[h] = csn[h];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          al[h][nt][0] = aln[h][nt][0]; al[h][nt][1] = aln[h][nt][1];
-          e[h][nt][0] = en[h][nt][0]; e[h][nt][1] = en[h][nt][1];
-        }
-        // prefetch for step t - 1: alpha^_{t-1}, and E_t / c_t (its "t + 1" quantities)
-        load_row(a.AL + r0[h] + (int64_t)(t[h] - 1) * N, N, q, t[h] > 0, 0.f, aln[h]);
+        for (int nt = 0; nt < NT; ++nt) { e[h][nt][0] = en[h][nt][0]; e[h][nt][1] = en[h][nt][1]; }
+        // alpha^_t is requested here and first used after this step's MMAs; E_t / c_t are step
+        // t - 1's "t + 1" quantities, needed BEFORE its MMAs, so they are fetched one step ahead
+        load_row(a.AL + r0[h] + (int64_t)t[h] * N, N, q, t[h] >= 0, 0.f, al[h]);
         load_row(a.E + r0[h] + (int64_t)t[h] * N, N, q, t[h] > 0, -INFINITY, en[h]);
         csn[h] = t[h] > 0 ? __ldg(a.cs + ri.pt[h] + t[h]) : 1.f;
       }
@@ -369,7 +380,7 @@ void launch_fb3(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) 
   Fb3Args a{c->dm.N, c->dm.Npad, c->t_A, c->t_pi, c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi};
   const int64_t groups = (s1 - s0 + 15) / 16;
   int64_t blocks = (groups + FB3_WARPS - 1) / FB3_WARPS;
-  const int64_t cap = (int64_t)c->sm_count * (backward ? DNBC_FB3_BWD_OCC : 3);
+  const int64_t cap = (int64_t)c->sm_count * (backward ? DNBC_FB3_BWD_OCC : DNBC_FB3_FWD_OCC);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (backward) k_backward3<<<(int)blocks, FB3_WARPS * 32, 0, c->stream>>>(a);
