@@ -470,6 +470,10 @@ static int64_t chunk_budget_points(const dnbc_ctx *c, size_t bytes_per_point) {
   size_t budget = std::min<size_t>((free_b + held) / 3, (size_t)48 << 30);
   int64_t pts = (int64_t)(budget / std::max<size_t>(bytes_per_point, 1));
   pts = std::min<int64_t>(pts, (int64_t)1 << 30);   // kernels index chunk-relative points with 32 bits
+  if (const char *cap = getenv("DNBC_MAX_CHUNK_POINTS")) {   // test hook: force the multi-chunk paths on small inputs
+    const long long v = atoll(cap);
+    if (v > 0) pts = std::min<int64_t>(pts, v);
+  }
   pts = std::max<int64_t>(pts, c->Tmax);
   return std::min<int64_t>(pts, std::max<int64_t>(c->P, 1));
 }

@@ -343,6 +343,48 @@ def test_streamed_estep_equals_upload_then_estep(oracle):
         assert abs(got[0] - ref[0]) <= TOL * abs(ref[0])
 
 
+def test_chunked_pipelines_equal_single_chunk(oracle, monkeypatch):
+    """The E-step, the streamed (upload-overlapped) E-step and the decoders walk the resident
+    sequences in chunks of whole sequences when the scratch does not hold them all.  With the
+    chunk size forced down to 300 points (DNBC_MAX_CHUNK_POINTS) every pipeline must reproduce
+    its single-chunk result on ragged sequences, for the FP32 and the tensor-core recursions."""
+    for N in (10, 64):
+        m = random_model(oracle, N, [5, 3], [2, 3], 700 + N, transitions_per_state=min(N, 8))
+        rng = np.random.default_rng(710 + N)
+        lengths = [int(x) for x in rng.integers(1, 120, 41)] + [1, 299, 300, 2]
+        data = sample(oracle, m, lengths, 720 + N)
+        q = perturb(oracle, m, 730 + N)
+        monkeypatch.delenv("DNBC_MAX_CHUNK_POINTS", raising=False)
+        with ctx_for(nat, q) as ctx:
+            upload(ctx, data, labels=False, dtype=np.float32)
+            ctx.em_estep()
+            want = ctx.em_get_stats()
+            g_want = ctx.em_posteriors()
+            p_want, s_want, t_want = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+            r_want, rs_want, _ = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+        monkeypatch.setenv("DNBC_MAX_CHUNK_POINTS", "300")
+        with ctx_for(nat, q) as ctx:
+            upload(ctx, data, labels=False, dtype=np.float32)
+            ctx.em_estep()
+            got = ctx.em_get_stats()
+            np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-5)   # fp32 windows group differently
+            np.testing.assert_allclose(ctx.em_posteriors(), g_want, rtol=1e-6, atol=1e-9)
+            ctx.em_estep_streamed(data.off, data.disc, data.cont.astype(np.float32))
+            np.testing.assert_allclose(ctx.em_get_stats(), want, rtol=2e-5, atol=1e-5)
+            p, sc, t = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+            np.testing.assert_array_equal(p, p_want)
+            np.testing.assert_array_equal(t, t_want)
+            np.testing.assert_allclose(sc, s_want, rtol=1e-12)
+            r, rs, _ = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+            np.testing.assert_array_equal(r, r_want)
+            np.testing.assert_allclose(rs, rs_want, rtol=1e-12)
+            ll = ctx.em_iterate(2)
+        monkeypatch.delenv("DNBC_MAX_CHUNK_POINTS")
+        with ctx_for(nat, q) as ctx:
+            upload(ctx, data, labels=False, dtype=np.float32)
+            np.testing.assert_allclose(ctx.em_iterate(2), ll, rtol=1e-7)
+
+
 def test_bridge_clamped_em_reproduces_supervised_learner(oracle):
     """One clamped EM iteration == the reference's supervised result: ties the
     Baum-Welch kernels, which have no reference counterpart, to DNBC.scala:124-220."""
