@@ -291,6 +291,12 @@ class Context:
         self._check(lib().dnbc_decode(self._h, mode, precision, _p(path), _p(score), _p(tie)))
         return path, score, tie
 
+    def decode_raw(self, mode: int, precision: int, path_ptr: int = 0, score_ptr: int = 0, tie_ptr: int = 0):
+        """dnbc_decode into caller-owned host buffers (u16 [P], f64 [S], u8 [P]; 0 = not wanted).
+        Pinned buffers make the result copies asynchronous DMA transfers."""
+        self._check(lib().dnbc_decode(self._h, mode, precision, C.c_void_p(path_ptr or None),
+                                      C.c_void_p(score_ptr or None), C.c_void_p(tie_ptr or None)))
+
     def synchronize(self):
         self._check(lib().dnbc_synchronize(self._h))
 
