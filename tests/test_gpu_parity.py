@@ -343,6 +343,28 @@ def test_streamed_estep_equals_upload_then_estep(oracle):
         assert abs(got[0] - ref[0]) <= TOL * abs(ref[0])
 
 
+@pytest.mark.parametrize("N", [10, 64, 300])
+def test_empty_sequences_between_real_ones(oracle, N):
+    """Zero-length sequences (leading, trailing, consecutive) in every recursion / decode path."""
+    m = random_model(oracle, N, [4], [2], 800 + N, transitions_per_state=min(N, 10))
+    lengths = [0, 5, 0, 0, 33, 1, 0, 17, 2, 0] * 4 + [0]
+    data = sample(oracle, m, lengths, 810 + N)
+    q = perturb(oracle, m, 820 + N)
+    want = oracle.estep(q, data)
+    opath, oscore, otie = oracle.decode(q, data, oracle.DECODE_BACKTRACE)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        p32, s32, t32 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    for key in ("pi", "xi", "gamma", "cat"):
+        np.testing.assert_allclose(sg[key], sw[key], rtol=1e-4, atol=1e-4, err_msg=key)
+    _paths_equal_except_ties(p32, opath, t32, otie, data.off)
+    np.testing.assert_allclose(s32, oscore, rtol=1e-5)
+
+
 def test_chunked_pipelines_equal_single_chunk(oracle, monkeypatch):
     """The E-step, the streamed (upload-overlapped) E-step and the decoders walk the resident
     sequences in chunks of whole sequences when the scratch does not hold them all.  With the
