@@ -102,22 +102,37 @@ struct EmitArgs {
 constexpr int EPU = 4;   // points per thread and coefficient fetch
 
 // one variable, EPU points: log2 mixture density added to acc[]
-template <int KP>
-__device__ __forceinline__ void emit_var(const float4 *ps, const float2 *pc, const float (&x)[EPU], float (&acc)[EPU]) {
+// kc = this variable's component count (warp-uniform): pairs past it are skipped, and the odd last
+// component is evaluated alone with scalar instructions -- K = 3 costs 3 exponentials, not 4.
+// VARK = false: every variable has exactly 2 KP components (no checks in the loop).
+template <int KP, bool VARK>
+__device__ __forceinline__ void emit_var(const float4 *ps, const float2 *pc, const float (&x)[EPU], float (&acc)[EPU], int kc) {
   const u64 neg1 = pk(-1.f, -1.f);
   u64 xx[EPU], sum2[EPU];
 #pragma unroll
-  for (int i = 0; i < EPU; ++i) xx[i] = pk(x[i], x[i]);
+  for (int i = 0; i < EPU; ++i) { xx[i] = pk(x[i], x[i]); sum2[i] = 0ull; }
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
+    if (VARK && 2 * kp >= kc) break;
     const float4 sm4 = ps[kp * 32];
     const float2 cc = pc[kp * 32];
-    const u64 s2 = pk(sm4.x, sm4.y), m2 = pk(sm4.z, sm4.w), cc2 = pk(cc.x, cc.y);
+    if (!VARK || 2 * kp + 1 < kc) {
+      const u64 s2 = pk(sm4.x, sm4.y), m2 = pk(sm4.z, sm4.w), cc2 = pk(cc.x, cc.y);
 #pragma unroll
-    for (int i = 0; i < EPU; ++i) {
-      const u64 z2 = fma2(xx[i], s2, m2);
-      const u64 e2 = ex2_2(fnma2(z2, z2, cc2));
-      sum2[i] = kp == 0 ? e2 : add2(sum2[i], e2);
+      for (int i = 0; i < EPU; ++i) {
+        const u64 z2 = fma2(xx[i], s2, m2);
+        const u64 e2 = ex2_2(fnma2(z2, z2, cc2));
+        sum2[i] = kp == 0 ? e2 : add2(sum2[i], e2);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) {
+        const float z = fmaf(x[i], sm4.x, sm4.z);
+        const float e = ex2_approx(fmaf(-z, z, cc.x));
+        float lo, hi;
+        unpk(sum2[i], lo, hi);
+        sum2[i] = pk(lo + e, hi);
+      }
     }
   }
 #pragma unroll
@@ -157,7 +172,7 @@ __device__ __forceinline__ void emit_var(const float4 *ps, const float2 *pc, con
 
 // shared-memory coefficient block of one 32-state slice: [C][KP][32] x {s.lo,s.hi,m.lo,m.hi} then
 // [C][KP][32] x {cc.lo,cc.hi}, then the categorical table [D][Vmax+1][32]
-template <int KP>
+template <int KP, bool VARK>
 __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
@@ -185,6 +200,8 @@ __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
     sm_sm[t] = make_float4(v[0], v[1], v[2], v[3]);
     sm_cc[t] = make_float2(v[4], v[5]);
   }
+  __shared__ int sK[64];                                     // components per continuous variable (C <= 64 here)
+  for (int t = threadIdx.x; t < C; t += blockDim.x) sK[t] = a.tb.K[t];
   for (int t = threadIdx.x; t < D * (Vmax + 1) * 32; t += blockDim.x) {
     const int sl = t & 31, v = (t >> 5) % (Vmax + 1), d = (t >> 5) / (Vmax + 1);
     const int j = jbase + sl % LG;
@@ -238,7 +255,7 @@ __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
         vp += P;
         if (c + 1 < C) ldx(xn);
         if (c + 1 < D) vn = __ldg((const uint32_t *)vp);
-        emit_var<KP>(ps, pc, xc, acc);
+        emit_var<KP, VARK>(ps, pc, xc, acc, sK[c]);
         ps += cstride;
         pc += cstride;
         if (c < D) add_cat(vc);
@@ -280,7 +297,7 @@ __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
     for (int c = 0; c < C; ++c) {
       if (c + 1 < C) load_x(c + 1, xn);
       if (c + 1 < D) vn = load_v(c + 1);
-      emit_var<KP>(ps, pc, xc, acc);
+      emit_var<KP, VARK>(ps, pc, xc, acc, sK[c]);
       ps += cstride;
       pc += cstride;
       if (c < D) add_cat(vc);
@@ -679,7 +696,7 @@ static size_t emit_smem(const Dims &d, int KP) {
 
 bool mixture_emission_fast(const dnbc_ctx *c) {
   const int KP = (c->dm.Kmax + 1) / 2;
-  return KP <= 4 && emit_smem(c->dm, KP) <= 100 * 1024;
+  return KP <= 4 && c->dm.C <= 64 && emit_smem(c->dm, KP) <= 100 * 1024;
 }
 // the statistics sweep keeps 3K coefficients + 3K accumulators in registers and handles one
 // continuous and one discrete variable per warp
@@ -691,8 +708,15 @@ bool mixture_stats_fast(const dnbc_ctx *c) {
 
 template <int KP>
 static void launch_emit_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem) {
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_emission_pk<KP><<<grid, 512, smem, c->stream>>>(a);
+  bool vark = false;                                         // some variable with fewer than 2 KP components?
+  for (int v = 0; v < c->dm.C; ++v) vark = vark || c->K[v] != 2 * KP;
+  if (vark) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_emission_pk<KP, true><<<grid, 512, smem, c->stream>>>(a);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_emission_pk<KP, false><<<grid, 512, smem, c->stream>>>(a);
+  }
 }
 
 void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
