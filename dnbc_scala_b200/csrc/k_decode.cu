@@ -19,6 +19,7 @@
 // every step (the shift is carried in fp64) so 1000-step sequences keep fp32 resolution;
 // T = double mirrors the JVM arithmetic operation by operation.
 #include "dnbc_internal.cuh"
+#include "packed_f32.cuh"
 
 #define DNBC_TIE_TOL_F32 1e-3f
 
@@ -236,17 +237,7 @@ __global__ void __launch_bounds__(256) k_decode(DecArgs<T> a) {
 //     per sequence but 10^5 sequences chase concurrently (~1 ms instead of ~10^2 sequential walks
 //     per warp).
 // ---------------------------------------------------------------------------------
-typedef unsigned long long vu64;
-__device__ __forceinline__ vu64 vpk(float lo, float hi) {
-  vu64 d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-  return d;
-}
-__device__ __forceinline__ void vadd2(vu64 a, vu64 b, float &lo, float &hi) {
-  vu64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
-}
+__device__ __forceinline__ void vadd2(u64 a, u64 b, float &lo, float &hi) { unpk(add2(a, b), lo, hi); }
 
 constexpr int VW = 4;   // warps per CTA
 void launch_backtrace(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const uint16_t *bp, uint16_t *path);
@@ -261,7 +252,7 @@ __global__ void __launch_bounds__(VW * 32) k_viterbi2(DecArgs<float> a) {
   const unsigned mask = dgroup_mask<LG>();
   bool act[R];
   int jr[R];
-  vu64 LA[R][NP / 2];
+  u64 LA[R][NP / 2];
   for (int q = threadIdx.x; q < NP * NP; q += blockDim.x) {
     const int i = q / NP, j = q % NP;
     sLA[q] = (i < N && j < N && a.active[i] && a.active[j]) ? a.logA[(int64_t)i * a.lda + j] : -INFINITY;
@@ -275,7 +266,7 @@ __global__ void __launch_bounds__(VW * 32) k_viterbi2(DecArgs<float> a) {
     jr[r] = lj + LG * r;
     act[r] = jr[r] < N && a.active[jr[r]] != 0;
 #pragma unroll
-    for (int i = 0; i < NP; i += 2) LA[r][i / 2] = vpk(sLA[i * NP + jr[r]], sLA[(i + 1) * NP + jr[r]]);
+    for (int i = 0; i < NP; i += 2) LA[r][i / 2] = pk(sLA[i * NP + jr[r]], sLA[(i + 1) * NP + jr[r]]);
   }
   float *svme = sv[w][gi];
   const float4 *sv4 = (const float4 *)svme;
@@ -313,7 +304,7 @@ __global__ void __launch_bounds__(VW * 32) k_viterbi2(DecArgs<float> a) {
 #pragma unroll
       for (int bk = 0; bk < NB; ++bk) {
         const float4 d = sv4[bk];
-        const vu64 d01 = vpk(d.x, d.y), d23 = vpk(d.z, d.w);
+        const u64 d01 = pk(d.x, d.y), d23 = pk(d.z, d.w);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           float c0, c1, c2, c3;

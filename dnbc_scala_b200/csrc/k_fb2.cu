@@ -16,6 +16,7 @@
 // ncu showed to be 90 % overhead instructions).  The per-step normaliser is a shuffle
 // reduction inside the group.  Groups are persistent and walk sequences with a grid stride.
 #include "dnbc_internal.cuh"
+#include "packed_f32.cuh"
 
 template <int LG>
 __device__ __forceinline__ unsigned gmask() {
@@ -52,22 +53,9 @@ struct Fb2Args {
 
 constexpr int FB_WARPS = 4;
 
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-  u64 d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-  return d;
-}
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
 __device__ __forceinline__ float hsum2(u64 a, u64 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+  unpk(add2(a, b), lo, hi);
   return lo + hi;
 }
 
@@ -84,17 +72,17 @@ __device__ __forceinline__ void matvec(const float *vec, const u64 (&M)[R][(NP +
 #pragma unroll
     for (int i4 = 0; i4 < NP / 4; ++i4) {
       const float4 v = v4[i4];
-      const u64 v01 = pk2(v.x, v.y), v23 = pk2(v.z, v.w);
+      const u64 v01 = pk(v.x, v.y), v23 = pk(v.z, v.w);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        part[r][0] = ffma2(v01, M[r][2 * i4], part[r][0]);
-        part[r][1] = ffma2(v23, M[r][2 * i4 + 1], part[r][1]);
+        part[r][0] = fma2(v01, M[r][2 * i4], part[r][0]);
+        part[r][1] = fma2(v23, M[r][2 * i4 + 1], part[r][1]);
       }
     }
   } else {                                                   // NP == 2
     const float2 v = *(const float2 *)vec;
 #pragma unroll
-    for (int r = 0; r < R; ++r) part[r][0] = ffma2(pk2(v.x, v.y), M[r][0], part[r][0]);
+    for (int r = 0; r < R; ++r) part[r][0] = fma2(pk(v.x, v.y), M[r][0], part[r][0]);
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) out[r] = hsum2(part[r][0], part[r][1]);
@@ -119,7 +107,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
     for (int i = 0; i < NP; i += 2) {
       const float lo = (i < N && jr[r] < N) ? a.tb.A[i * Npad + jr[r]] : 0.f;
       const float hi = (i + 1 < N && jr[r] < N) ? a.tb.A[(i + 1) * Npad + jr[r]] : 0.f;
-      Acol[r][i / 2] = pk2(lo, hi);
+      Acol[r][i / 2] = pk(lo, hi);
     }
   }
   const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;
@@ -229,7 +217,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
     for (int jj = 0; jj < NP; jj += 2) {
       const float lo = (jj < N && ir[r] < N) ? a.tb.A[ir[r] * Npad + jj] : 0.f;
       const float hi = (jj + 1 < N && ir[r] < N) ? a.tb.A[ir[r] * Npad + jj + 1] : 0.f;
-      Arow[r][jj / 2] = pk2(lo, hi);
+      Arow[r][jj / 2] = pk(lo, hi);
     }
   }
   const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;

@@ -30,44 +30,8 @@
 //     categorical bins live in warp-private shared-memory columns (no atomics); each window
 //     ends with one fp64 atomicAdd per statistic.
 #include "dnbc_internal.cuh"
+#include "packed_f32.cuh"
 
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 pk(float lo, float hi) {
-  u64 d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-  return d;
-}
-__device__ __forceinline__ void unpk(u64 v, float &lo, float &hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-  u64 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// c - a * b, packed: the negation is written on the halves so that ptxas folds it into the FFMA2
-__device__ __forceinline__ u64 fnma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("{\n\t.reg .f32 lo, hi;\n\t.reg .b64 n;\n\tmov.b64 {lo, hi}, %1;\n\tneg.f32 lo, lo;\n\tneg.f32 hi, hi;\n\t"
-      "mov.b64 n, {lo, hi};\n\tfma.rn.f32x2 %0, n, %2, %3;\n\t}" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
 __device__ __forceinline__ u64 ex2_2(u64 a) {
   u64 d;
   asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tex2.approx.ftz.f32 lo, lo;\n\tex2.approx.ftz.f32 hi, hi;\n\t"

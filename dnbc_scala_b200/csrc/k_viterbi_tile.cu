@@ -21,6 +21,7 @@
 //     recovered afterwards by re-forming just those 4 candidates (bit-identical adds);
 //   * the back-trace is k_backtrace (k_decode.cu): one thread per sequence.
 #include "dnbc_internal.cuh"
+#include "packed_f32.cuh"
 
 #define DNBC_TIE_TOL_F32 1e-3f
 
@@ -31,13 +32,9 @@ constexpr int VT_BS = 32;     // sequences per CTA
 constexpr int VT_JC = 256;    // destinations per pass
 constexpr int VT_IT = 32;     // sources per shared-memory tile
 
-typedef unsigned long long vu64;
+// (lo, hi) + (s, s)
 __device__ __forceinline__ void add2s(float lo, float hi, float s, float &olo, float &ohi) {
-  vu64 a, b, d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(lo), "f"(hi));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(s));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(olo), "=f"(ohi) : "l"(d));
+  unpk(add2(pk(lo, hi), pk(s, s)), olo, ohi);
 }
 __device__ __forceinline__ void cp16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
