@@ -231,6 +231,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
       } else {
         // ---- beta_t in TMEM (1 on the last step); gamma = alpha * beta; next u = exp(E_t - m_t) beta / c_t ----
         const float ic = live ? 1.0f / a.cs[p] : 0.f;
+        // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
+        // ~1e-5 per step, so beta^_t is rescaled to make it 1 at every step (as k_fb2 / k_fb3 do)
+        float fix = 1.f;
+        {
+          float s = 0.f;
+          for (int ch = 0; ch < ncol / 32; ++ch) {
+            const int c0 = col0 + ch * 32;
+            float d[32], al[32];
+            if (k > 0) tmem_ld32(trow + c0, d);
+            else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d[i] = 1.f;
+            }
+            load32(a.AL + p * N, c0, N, vec, live, 0.f, al);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s = fmaf(al[i], d[i], s);
+          }
+          rsum[row][half] = s;
+          __syncthreads();
+          s = rsum[row][0] + rsum[row][1];
+          fix = (live && s > 0.f) ? 1.0f / s : 1.f;
+        }
         for (int ch = 0; ch < ncol / 32; ++ch) {
           const int c0 = col0 + ch * 32;
           float d[32], e[32], al[32];
@@ -239,6 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) d[i] = 1.f;
           }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d[i] *= fix;
           load32(Erow, c0, N, vec, live, -INFINITY, e);
           load32(a.AL + p * N, c0, N, vec, live, 0.f, al);
 #pragma unroll
