@@ -30,7 +30,7 @@ def one(case, rng):
     tps = int(rng.integers(1, min(N, 12) + 1))
     m = random_model(oracle, N, V, K, int(rng.integers(1 << 30)), transitions_per_state=tps, unit_var=bool(rng.integers(2)))
     nseq = int(rng.integers(1, 50))
-    tmax = int(rng.choice([1, 3, 20, 90]))
+    tmax = int(rng.choice([1, 3, 20, 90, 400] if os.environ.get("FUZZ_LONG") else [1, 3, 20, 90]))
     lengths = [int(x) for x in rng.integers(0, tmax + 1, nseq)]
     if sum(lengths) == 0:
         lengths[0] = 2
