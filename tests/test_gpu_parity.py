@@ -315,6 +315,10 @@ def test_randomised_shapes_against_the_oracle():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "60", "2026"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    # supervised learner (counts with both quirk flags, k-means, per-edge GMM EM) + REFERENCE decode
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "30", "2027", "mle"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("N,V,K,S,T", [(10, [10] * 5, [3, 1, 4, 2, 3], 64, 200), (12, [4], [], 48, 200), (10, [], [3] * 5, 64, 200)])
