@@ -212,3 +212,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 src = open(os.path.join(root, f)).read()
                 assert not pat.search(src), f
+
+
+def test_jni_glue_type_checks_against_the_abi():
+    """jni/dnbc_b200_jni.c (the glue a maintainer compiles against a real JDK) must at least
+    agree with include/dnbc_b200.h: it is type-checked here against a minimal jni.h stub, and every native it
+    defines must be declared in jni/NativeDnbc.scala."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    glue = os.path.join(root, "jni", "dnbc_b200_jni.c")
+    out = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                          "-I" + os.path.join(root, "tests", "jni_stub"), "-I" + os.path.join(root, "include"), glue],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    natives_c = set(re.findall(r"Java_NativeDnbc_(n\w+)", open(glue).read()))
+    natives_scala = set(re.findall(r"@native private def (n\w+)", open(os.path.join(root, "jni", "NativeDnbc.scala")).read()))
+    assert natives_c == natives_scala and len(natives_c) >= 14, (natives_c ^ natives_scala)
