@@ -1,5 +1,5 @@
 """Randomised parity sweep: random shapes / mixtures / ragged lengths, CUDA path vs the fp64 oracle.
-usage: python tools/fuzz_parity.py [cases] [seed]   (needs a B200; prints the first failure and exits 1)"""
+usage: python tests/fuzz_parity.py [cases] [seed]   (needs a B200; prints the first failure and exits 1)"""
 import os
 import sys
 

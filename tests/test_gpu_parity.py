@@ -306,17 +306,17 @@ def test_every_state_count_dispatch_path_matches_oracle(oracle, N):
 
 
 def test_randomised_shapes_against_the_oracle():
-    """tools/fuzz_parity.py: 60 seeded random shapes (1..300 states, 0..3 + 0..3 variables, mixtures of
+    """tests/fuzz_parity.py: 60 seeded random shapes (1..300 states, 0..3 + 0..3 variables, mixtures of
     1..8 components, sparse transitions, ragged and empty sequences) -- E-step statistics, posteriors and
     all three decoders against the fp64 oracle."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "60", "2026"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_parity.py"), "60", "2026"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     # supervised learner (counts with both quirk flags, k-means, per-edge GMM EM) + REFERENCE decode
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "30", "2027", "mle"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_parity.py"), "30", "2027", "mle"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
