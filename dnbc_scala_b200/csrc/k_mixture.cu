@@ -515,13 +515,13 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *b
     }
   }
   if (GSUM) gs += (double)gsl;
-  if (HAS_C && (DNBC_STATS_FAST || DNBC_STATS_PIPE) && __any_sync(0xffffffffu, bad)) {
+  if (HAS_C && (DNBC_STATS_FAST || DNBC_STATS_PIPE) && __any_sync(0xffffffffu, bad && jon)) {
     // rare: some point of this block sits where a state's whole mixture underflows fp32.  Redo the
     // block through the shifted evaluation, each lane contributing only where its fast path gave up
     // (the test below repeats stat_point_fast's: same inputs, same instructions, same outcome).
 #pragma unroll 1
     for (int st = 0; st < LG; ++st) {
-      const bool on = fast || (base + st * PG + lp < pe && jon);
+      const bool on = jon && (fast || base + st * PG + lp < pe);
       const float g = on ? __ldg(gp0 + (int64_t)st * gstep) : 0.f;
       const float x = __shfl_sync(0xffffffffu, xreg, st * PG + lp);
       StatRegs<KP> probe = q;
@@ -592,7 +592,9 @@ __global__ void __launch_bounds__(DNBC_STATS_NW * 32, DNBC_STATS_OCC) k_stats_pk
       if (has_d) vnext = (int)__ldg(dcol + base + 32 + lane);
     }
     const float *gp = gcol + (int64_t)(base + lp) * N;      // posterior of this lane's state, step 0
-    const bool fast = full && jon && LG >= SPB;
+    // warp-uniform: padded lanes (j >= N) run the same predicate-free path on state 0's posteriors and
+    // their accumulators are never flushed (a per-lane flag made the warp execute BOTH block variants)
+    const bool fast = full && LG >= SPB;
 #define STAT_BLOCK(C_, D_, G_)                                                                          \
   do {                                                                                                 \
     if (fast) stat_block<KP, C_, D_, G_, true>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, base, pe, jon);   \
