@@ -693,7 +693,7 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   const int vec = (c->P % 4 == 0) && (p0 % 4 == 0);
   EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, d.Npad < 32 ? d.Npad : 32, vec};
   const size_t smem = emit_smem(d, KP);
-  const int gy = (d.Npad + 31) / 32;
+  const int gy = (d.N + 31) / 32;                          // slices of 32 states that hold a real state
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
@@ -720,7 +720,7 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
   int units = d.C > d.D ? d.C : d.D;
   if (units < 1) units = 1;
   const int NW = units > DNBC_STATS_NW ? DNBC_STATS_NW : units;
-  const int gz = (units + NW - 1) / NW, gy = (d.Npad + 31) / 32;
+  const int gz = (units + NW - 1) / NW, gy = (d.N + 31) / 32;
   StatArgs a{d, c->tables(), c->data(), p0, (int)np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
              c->d_stats + sl.gamma, d.Npad < 32 ? d.Npad : 32, NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
