@@ -11,12 +11,16 @@
 //     product is formed as hi*hi + hi*lo + lo*hi into the same fp32 accumulator (relative
 //     error ~2^-16 per term; a single bf16 pass would be ~2^-9, far outside the 1e-5 budget);
 //   * the transition matrix (K-major, [to][from] for the forward pass, [from][to] for the
-//     backward pass) streams from L2 in 64-wide K blocks through a 2-stage shared-memory ring
-//     in the canonical 128-byte-swizzled K-major layout (cp.async 16-byte chunks, XOR
-//     swizzle); one thread issues the tcgen05.mma's and commits to an mbarrier per stage;
+//     backward pass) is kept in global memory as ready-made images of the 128-byte-swizzled
+//     K-major shared-memory tiles (k_tc_tables), and so is the staging copy of the step's
+//     operand X; a producer thread streams them from L2 in 64-wide K blocks through a 2-stage
+//     ring with bulk async copies (cp.async.bulk, completion counted on an mbarrier), a
+//     second thread issues the tcgen05.mma's and commits to an mbarrier per stage and per
+//     256-column half of the accumulator;
 //   * the epilogue (8 warps, thread = (sequence row, half of the columns)) reads TMEM with
 //     tcgen05.ld, applies the emission, normalises the row, writes alpha / gamma / u to HBM and
-//     the next step's split operand to an L2-resident staging tile.
+//     the next step's split operand to the L2-resident staging tiles.  The warps of the first
+//     column half start while the MMAs of the second half are still running.
 // The step-to-step dependency (the epilogue of step t feeds the MMA of step t+1) serialises
 // MMA and epilogue within a CTA; 148 CTAs keep all SMs busy on independent batches.
 #include <cuda_bf16.h>
@@ -29,21 +33,26 @@ namespace {
 constexpr int TC_M = 128;          // sequences per CTA batch (UMMA M)
 constexpr int TC_NH = 256;         // UMMA N per instruction
 constexpr int TC_KB = 64;          // K block (one 128-byte swizzled row of bf16)
-constexpr int TC_THREADS = 256;
+constexpr int TC_EPI = 256;        // epilogue threads (warps 0-7)
+constexpr int TC_THREADS = 320;    // + warp 8 (lane 0: bulk-copy producer) + warp 9 (lane 0: MMA issuer)
 constexpr int A_TILE = TC_M * TC_KB * 2;    // 16 KB
 constexpr int B_TILE = TC_NH * TC_KB * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;   // hi + lo of both operands: 96 KB
+constexpr uint32_t BULK = 16 * 1024;        // bytes per bulk copy
 
-// rows x 64 bf16 tile: global row-major (ld elements per row) -> swizzled shared memory
-__device__ __forceinline__ void load_tile(uint32_t tile, const __nv_bfloat16 *g, int rows, int ld) {
-  for (int idx = threadIdx.x; idx < rows * 8; idx += TC_THREADS) {
-    const int r = idx >> 3, c = idx & 7;
-    cp_async16(tile + sw128(r, c), g + (size_t)r * ld + c * 8);
-  }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// global -> shared bulk async copy (TMA unit, no tensor map: source and destination are contiguous)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI) : "memory"); }
 
-// split 32 fp32 values into bf16 hi / lo and store both (64 B each) to the staging rows
-__device__ __forceinline__ void store_split(const float (&x)[32], __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+// split 32 fp32 values (row r, columns c0 .. c0+31 of X) into bf16 hi / lo and store them into the staging
+// copy, which is laid out as the shared-memory images of the K-block tiles: [kb][hi | lo][128 x 64 swizzled]
+__device__ __forceinline__ void store_split(const float (&x)[32], unsigned char *xt, int r, int c0) {
   uint32_t h[16], l[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -53,10 +62,13 @@ __device__ __forceinline__ void store_split(const float (&x)[32], __nv_bfloat16 
     h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
     l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
   }
+  unsigned char *tile = xt + (size_t)(c0 >> 6) * (2 * A_TILE);
+  const int cb = (c0 & 63) >> 3;                            // first 16-byte chunk of the row: 0 or 4
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    ((uint4 *)hi)[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-    ((uint4 *)lo)[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+    const uint32_t o = sw128(r, cb + i);
+    *(uint4 *)(tile + o) = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    *(uint4 *)(tile + A_TILE + o) = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
   }
 }
 
@@ -94,70 +106,81 @@ struct TcArgs {
   double *stats;
   int64_t st_pi;
   const float *pi;              // [N]
-  const __nv_bfloat16 *Bh, *Bl; // [NP][NP] K-major operand B (forward: A^T, backward: A)
-  __nv_bfloat16 *Xh, *Xl;       // [grid][128][NP] staging of the next step's operand A
+  const unsigned char *Bt;      // operand B (forward: A^T, backward: A) as tile images: [nh][kb][hi | lo][256 x 64]
+  unsigned char *Xt;            // [grid] staging of the next step's operand X as tile images: [kb][hi | lo][128 x 64]
 };
 
-// D[128][NP] (TMEM) = X[128][NP] * B^T, X from the staging tile, B streamed from global
-__device__ void tc_gemm(const TcArgs &a, uint32_t smem_base, uint32_t bar0, uint32_t tmem, uint32_t (&uses)[2],
-                        const __nv_bfloat16 *xh, const __nv_bfloat16 *xl) {
-  const int NP = a.NP, nkb = NP / TC_KB, nnh = NP / TC_NH;
+// Producer (one thread): stream the K-block tiles of X and B for one step into the ring.
+__device__ void tc_produce(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty, uint32_t (&uses)[2],
+                           const unsigned char *xt) {
+  const int nkb = a.NP / TC_KB, nnh = a.NP / TC_NH;
+  int it = 0;
+  for (int nh = 0; nh < nnh; ++nh) {
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int s = it & 1;
+      const uint32_t st = smem_base + s * STAGE_BYTES, full = bar_full + 8 * s;
+      // the stage is free once the MMAs that read its previous contents have completed
+      if (uses[s] > 0) mbar_wait(bar_empty + 8 * s, (uses[s] - 1) & 1);
+      mbar_expect_tx(full, STAGE_BYTES);
+      const unsigned char *xs = xt + (size_t)kb * (2 * A_TILE);
+      const unsigned char *bs = a.Bt + ((size_t)nh * nkb + kb) * (2 * B_TILE);
+#pragma unroll
+      for (uint32_t o = 0; o < 2 * A_TILE; o += BULK) bulk_g2s(st + o, xs + o, BULK, full);
+#pragma unroll
+      for (uint32_t o = 0; o < 2 * B_TILE; o += BULK) bulk_g2s(st + 2 * A_TILE + o, bs + o, BULK, full);
+      uses[s] += 1;
+    }
+  }
+}
+
+// MMA issuer (one thread): D[128][NP] (TMEM) = X[128][NP] * B^T, 256 accumulator columns at a time
+__device__ void tc_mma(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_done,
+                       uint32_t tmem, uint32_t (&uses)[2]) {
+  const int nkb = a.NP / TC_KB, nnh = a.NP / TC_NH;
   const uint32_t idesc = umma_idesc(TC_M, TC_NH);
   int it = 0;
   for (int nh = 0; nh < nnh; ++nh) {
     for (int kb = 0; kb < nkb; ++kb, ++it) {
       const int s = it & 1;
       const uint32_t st = smem_base + s * STAGE_BYTES;
-      // the stage is free once the MMAs that read it two iterations ago have completed
-      if (uses[s] > 0) mbar_wait(bar0 + 8 * s, (uses[s] - 1) & 1);
-      load_tile(st, xh + kb * TC_KB, TC_M, NP);
-      load_tile(st + A_TILE, xl + kb * TC_KB, TC_M, NP);
-      load_tile(st + 2 * A_TILE, a.Bh + (size_t)nh * TC_NH * NP + kb * TC_KB, TC_NH, NP);
-      load_tile(st + 2 * A_TILE + B_TILE, a.Bl + (size_t)nh * TC_NH * NP + kb * TC_KB, TC_NH, NP);
-      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        const uint64_t dAh = umma_desc(st), dAl = umma_desc(st + A_TILE);
-        const uint64_t dBh = umma_desc(st + 2 * A_TILE), dBl = umma_desc(st + 2 * A_TILE + B_TILE);
-        const uint32_t d = tmem + nh * TC_NH;
+      mbar_wait(bar_full + 8 * s, uses[s] & 1);
+      tc_fence_after();
+      const uint64_t dAh = umma_desc(st), dAl = umma_desc(st + A_TILE);
+      const uint64_t dBh = umma_desc(st + 2 * A_TILE), dBl = umma_desc(st + 2 * A_TILE + B_TILE);
+      const uint32_t d = tmem + nh * TC_NH;
 #pragma unroll
-        for (int k16 = 0; k16 < TC_KB / 16; ++k16) {
-          const uint64_t ko = (uint64_t)(k16 * 32 >> 4);     // 16 bf16 = 32 B further along K
-          umma_bf16(d, dAh + ko, dBh + ko, idesc, (kb | k16) ? 1u : 0u);
-          umma_bf16(d, dAh + ko, dBl + ko, idesc, 1u);
-          umma_bf16(d, dAl + ko, dBh + ko, idesc, 1u);
-        }
-        umma_commit(bar0 + 8 * s);
+      for (int k16 = 0; k16 < TC_KB / 16; ++k16) {
+        const uint64_t ko = (uint64_t)(k16 * 32 >> 4);     // 16 bf16 = 32 B further along K
+        umma_bf16(d, dAh + ko, dBh + ko, idesc, (kb | k16) ? 1u : 0u);
+        umma_bf16(d, dAh + ko, dBl + ko, idesc, 1u);
+        umma_bf16(d, dAl + ko, dBh + ko, idesc, 1u);
       }
+      umma_commit(bar_empty + 8 * s);
+      if (kb == nkb - 1) umma_commit(bar_done + 8 * nh);   // this half of the accumulator is complete
       uses[s] += 1;
     }
   }
-  // all MMAs of this step have landed in TMEM
-  for (int s = 0; s < 2; ++s)
-    if (uses[s] > 0) mbar_wait(bar0 + 8 * s, (uses[s] - 1) & 1);
-  tc_fence_after();
 }
 
 template <int DIR>   // 0 = forward, 1 = backward
 __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
   extern __shared__ unsigned char smraw[];
-  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ __align__(8) unsigned long long bars[6];        // full[2], empty[2], done[2]
   __shared__ uint32_t tmem_slot;
   __shared__ float rsum[TC_M][2];
   __shared__ int sT[TC_M];
   __shared__ int sTmax;
   const int N = a.N, NP = a.NP;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int row = (w & 3) * 32 + lane, half = w >> 2;        // TMEM lane quadrant = warp % 4
+  const bool epi = w < TC_EPI / 32;
+  const int row = (w & 3) * 32 + lane, half = (w >> 2) & 1;  // TMEM lane quadrant = warp % 4
   const int ncol = NP / 2, col0 = half * ncol;               // this thread's column range
   const bool vec = (N % 4) == 0 && N == NP;                  // rows are whole float4's and no padded columns
   const uint32_t smem_base = (smem_u32(smraw) + 1023u) & ~1023u;
-  const uint32_t bar0 = smem_u32(&bars[0]);
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[2]), bar_done = smem_u32(&bars[4]);
+  const uint32_t my_done = bar_done + 8 * (col0 / TC_NH);    // the accumulator half this thread's columns are in
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    for (int i = 0; i < 6; ++i) mbar_init(bar_full + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (w == 0) {
@@ -170,23 +193,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
   const uint32_t tmem = tmem_slot;
   const uint32_t trow = tmem + ((uint32_t)((w & 3) * 32) << 16);
   uint32_t uses[2] = {0u, 0u};
-  __nv_bfloat16 *xh = a.Xh + (size_t)blockIdx.x * TC_M * NP, *xl = a.Xl + (size_t)blockIdx.x * TC_M * NP;
+  uint32_t gsteps = 0;                                       // products issued so far (parity of the done barriers)
+  unsigned char *xt = a.Xt + (size_t)blockIdx.x * TC_M * NP * 4;   // hi + lo, 2 bytes each
   double ll = 0.0;
 
   for (int64_t sb = a.s0 + (int64_t)blockIdx.x * TC_M; sb < a.s1; sb += (int64_t)gridDim.x * TC_M) {
     const int64_t s = sb + row;
-    const int T = s < a.s1 ? (int)(a.off[s + 1] - a.off[s]) : 0;
-    const int64_t pt = s < a.s1 ? a.off[s] - a.p0 : 0;
+    const int T = (epi && s < a.s1) ? (int)(a.off[s + 1] - a.off[s]) : 0;
+    const int64_t pt = (epi && s < a.s1) ? a.off[s] - a.p0 : 0;
     if (tid == 0) sTmax = 0;
     __syncthreads();
-    if (half == 0) { sT[row] = T; atomicMax(&sTmax, T); }
+    if (epi && half == 0) { sT[row] = T; atomicMax(&sTmax, T); }
     __syncthreads();
     const int Tmax = sTmax;
     for (int k = 0; k < Tmax; ++k) {
+      if (!epi) {
+        // ---- warp 8: producer, warp 9: MMA issuer (one elected lane each)
+        if (k > 0 && lane == 0) {
+          if (w == TC_EPI / 32) tc_produce(a, smem_base, bar_full, bar_empty, uses, xt);
+          else {
+            tc_fence_after();
+            tc_mma(a, smem_base, bar_full, bar_empty, bar_done, tmem, uses);
+          }
+        }
+        __syncwarp();
+      } else {
       // forward walks t = k; backward walks t = T - 1 - k (rows aligned at their last step)
       const int t = DIR == 0 ? k : T - 1 - k;
       const bool live = DIR == 0 ? (k < T) : (t >= 0);
-      if (k > 0) tc_gemm(a, smem_base, bar0, tmem, uses, xh, xl);
       const int64_t p = pt + (live ? t : 0);
       const float *Erow = a.E + p * N;
       const float mx = live ? a.mrow[p] : 0.f;
@@ -196,6 +230,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
         float sum = 0.f;
         float e[32], en[32];
         load32(Erow, col0, N, vec, live, -INFINITY, en);           // emission rows are fetched one chunk ahead
+        if (live && vec) {                                         // ... and the rest of the row is pulled into L2
+#pragma unroll 1
+          for (int c = col0 + 32; c < col0 + ncol; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
+        }
+        if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
         for (int ch = 0; ch < ncol / 32; ++ch) {
           const int c0 = col0 + ch * 32;
           float d[32];
@@ -212,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           tmem_st32(trow + c0, d);
         }
         rsum[row][half] = sum;
-        __syncthreads();
+        epi_sync();
         const float c = rsum[row][0] + rsum[row][1];
         const float inv = live ? 1.0f / c : 0.f;
         for (int ch = 0; ch < ncol / 32; ++ch) {
@@ -222,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) d[i] *= inv;
           if (live) store32(a.AL + p * N, c0, N, vec, d);
-          store_split(d, xh + (size_t)row * NP + c0, xl + (size_t)row * NP + c0);
+          store_split(d, xt, row, c0);
         }
         if (live && half == 0) {
           a.cs[p] = c;
@@ -231,6 +270,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
       } else {
         // ---- beta_t in TMEM (1 on the last step); gamma = alpha * beta; next u = exp(E_t - m_t) beta / c_t ----
         const float ic = live ? 1.0f / a.cs[p] : 0.f;
+        if (live && vec) {                                         // this step's alpha and emission rows -> L2
+#pragma unroll 1
+          for (int c = col0; c < col0 + ncol; c += 32) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.AL + p * N + c));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
+          }
+        }
+        if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
         // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
         // ~1e-5 per step, so beta^_t is rescaled to make it 1 at every step (as k_fb2 / k_fb3 do)
         float fix = 1.f;
@@ -249,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
             for (int i = 0; i < 32; ++i) s = fmaf(al[i], d[i], s);
           }
           rsum[row][half] = s;
-          __syncthreads();
+          epi_sync();
           s = rsum[row][0] + rsum[row][1];
           fix = (live && s > 0.f) ? 1.0f / s : 1.f;
         }
@@ -285,16 +332,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
               store32(a.U + p * N, c0, N, vec, z);
             }
           }
-          store_split(e, xh + (size_t)row * NP + c0, xl + (size_t)row * NP + c0);
+          store_split(e, xt, row, c0);
         }
       }
-      // TMEM reads done and the staging tile visible before the next step's MMAs / loads
+      // the staging tiles are read by the bulk copies (async proxy) of the next step
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      }
+      if (k > 0) gsteps += 1;
+      // TMEM reads done and the staging tiles visible before the next step's MMAs / loads
       tc_fence_before();
       __threadfence();
       __syncthreads();
     }
   }
-  if (DIR == 0 && half == 0 && ll != 0.0) atomicAdd(a.stats, ll);
+  if (epi && DIR == 0 && half == 0 && ll != 0.0) atomicAdd(a.stats, ll);
   tc_fence_before();
   __syncthreads();
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
@@ -312,18 +363,21 @@ __global__ void k_rowmax(const float *__restrict__ E, int N, int64_t np, float *
   }
 }
 
-// bf16 split tables of the transition matrix: TA = [from][to] (backward), TAt = [to][from] (forward)
-__global__ void k_tc_tables(const double *__restrict__ A, int N, int NP, __nv_bfloat16 *Ah, __nv_bfloat16 *Al,
-                            __nv_bfloat16 *Ath, __nv_bfloat16 *Atl) {
+// bf16 split tables of the transition matrix as shared-memory tile images (what a bulk copy drops into a
+// ring stage): operand row n, reduction index k -> tile (n / 256, k / 64), [hi | lo], 128-byte swizzled row.
+// Tb = [from][to] (backward: n = from, k = to), Tf = [to][from] (forward: n = to, k = from).
+__global__ void k_tc_tables(const double *__restrict__ A, int N, int NP, unsigned char *Tb, unsigned char *Tf) {
+  const int nkb = NP / TC_KB;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < (int64_t)NP * NP; q += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(q / NP), c = (int)(q % NP);
     const float v = (r < N && c < N) ? (float)A[(int64_t)r * N + c] : 0.f;
     const float vt = (r < N && c < N) ? (float)A[(int64_t)c * N + r] : 0.f;
     const __nv_bfloat16 h = __float2bfloat16_rn(v), ht = __float2bfloat16_rn(vt);
-    Ah[q] = h;
-    Al[q] = __float2bfloat16_rn(v - __bfloat162float(h));
-    Ath[q] = ht;
-    Atl[q] = __float2bfloat16_rn(vt - __bfloat162float(ht));
+    const size_t o = ((size_t)(r / TC_NH) * nkb + c / TC_KB) * (2 * B_TILE) + sw128(r % TC_NH, (c % TC_KB) >> 3) + (c & 7) * 2;
+    *(__nv_bfloat16 *)(Tb + o) = h;
+    *(__nv_bfloat16 *)(Tb + o + B_TILE) = __float2bfloat16_rn(v - __bfloat162float(h));
+    *(__nv_bfloat16 *)(Tf + o) = ht;
+    *(__nv_bfloat16 *)(Tf + o + B_TILE) = __float2bfloat16_rn(vt - __bfloat162float(ht));
   }
 }
 
@@ -340,9 +394,9 @@ void launch_tc_tables(dnbc_ctx *c) {
   if (!c->tc_tab) {
     if (cudaMalloc((void **)&c->tc_tab, 4 * n * sizeof(__nv_bfloat16)) != cudaSuccess) return;
   }
-  __nv_bfloat16 *t = (__nv_bfloat16 *)c->tc_tab;
+  unsigned char *t = (unsigned char *)c->tc_tab;
   c->launches++;
-  k_tc_tables<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_A, c->dm.N, NP, t, t + n, t + 2 * n, t + 3 * n);
+  k_tc_tables<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_A, c->dm.N, NP, t, t + 4 * n);
 }
 
 int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bool backward) {
@@ -361,11 +415,10 @@ int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bo
     if (cudaMalloc((void **)&c->tc_mrow, (size_t)np * sizeof(float)) != cudaSuccess) return DNBC_ENOMEM;
     c->tc_mrow_cap = np;
   }
-  __nv_bfloat16 *t = (__nv_bfloat16 *)c->tc_tab;
+  const unsigned char *t = (const unsigned char *)c->tc_tab;
   StatsLayout sl = stats_layout(c->dm);
   TcArgs a{N, NP, c->d_off, s0, s1, p0, c->E, c->tc_mrow, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi, c->t_pi,
-           backward ? t : t + 2 * n, backward ? t + n : t + 3 * n,
-           (__nv_bfloat16 *)c->tc_x, (__nv_bfloat16 *)((char *)c->tc_x + xbytes)};
+           backward ? t : t + 4 * n, (unsigned char *)c->tc_x};
   const size_t smem = 2 * STAGE_BYTES + 1024;
   if (!backward) {
     c->launches++;
