@@ -96,6 +96,78 @@ __device__ __forceinline__ void store32(float *g, int j0, int N, bool vec, const
   }
 }
 
+// ---- coalesced global traffic for the epilogue ----------------------------------------------------
+// An epilogue thread owns one sequence row (its TMEM lane), but a warp-wide access in which every lane
+// touches a different row costs one LSU cycle per row.  32 x 32 fp32 chunks therefore go through a
+// warp-private 4 KB shared-memory tile (16-byte slots XOR-swizzled by the row, conflict-free both ways):
+// global accesses are made with lane = (row it*4 + lane/8, 16-byte slot lane%8), i.e. 4 rows x 128
+// contiguous bytes per instruction, and the tile is read / written by row on the other side.
+constexpr int TB_BYTES = 32 * 128;
+__device__ __forceinline__ uint32_t tb_off(int r, int c4) { return (uint32_t)(r * 128 + ((c4 ^ (r & 7)) << 4)); }
+
+// issue the loads of columns col .. col+31 of the warp's 32 rows (pp = point index of row it*4 + lane/8)
+__device__ __forceinline__ void chunk_ldg(const float *base, const int (&pp)[8], unsigned mask, int N, int col, int lane,
+                                          float fill, float4 (&q)[8]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    q[it] = ((mask >> rr) & 1u) ? __ldg((const float4 *)(base + (int64_t)pp[it] * N + col) + (lane & 7))
+                                : make_float4(fill, fill, fill, fill);
+  }
+}
+// ... and hand every thread the 32 values of its own row
+__device__ __forceinline__ void chunk_to_rows(unsigned char *tb, int lane, const float4 (&q)[8], float (&v)[32]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) *(float4 *)(tb + tb_off(it * 4 + (lane >> 3), lane & 7)) = q[it];
+  __syncwarp();
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 x = *(const float4 *)(tb + tb_off(lane, c4));
+    v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void rows_to_tb(unsigned char *tb, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4)
+    *(float4 *)(tb + tb_off(lane, c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+  __syncwarp();
+}
+// tile -> rows (pp[it] + drow) of a row-major fp32 array, columns col .. col+31, rows selected by mask
+__device__ __forceinline__ void tb_store_f32(const unsigned char *tb, float *base, const int (&pp)[8], unsigned mask, int N,
+                                             int col, int lane, int drow) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    if ((mask >> rr) & 1u)
+      *((float4 *)(base + (int64_t)(pp[it] + drow) * N + col) + (lane & 7)) = *(const float4 *)(tb + tb_off(rr, lane & 7));
+  }
+}
+// tile -> bf16 hi / lo split into the staging tile images (rows row0 .. row0+31, columns c0 .. c0+31 of X):
+// lane = (row it*8 + lane/4, 8 columns lane%4), one 16-byte store each for hi and lo
+__device__ __forceinline__ void tb_store_split(const unsigned char *tb, unsigned char *xt, int row0, int c0, int lane) {
+  unsigned char *tile = xt + (size_t)(c0 >> 6) * (2 * A_TILE);
+  const int cb = (c0 & 63) >> 3, i = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2);
+    const float4 u = *(const float4 *)(tb + tb_off(rr, 2 * i)), v = *(const float4 *)(tb + tb_off(rr, 2 * i + 1));
+    const float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * e]), h1 = __float2bfloat16_rn(x[2 * e + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * e] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * e + 1] - __bfloat162float(h1));
+      h[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      l[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const uint32_t o = sw128(row0 + rr, cb + i);
+    *(uint4 *)(tile + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *(uint4 *)(tile + A_TILE + o) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 struct TcArgs {
   int N, NP;                    // states, padded states (256 or 512)
   const int64_t *off;
@@ -162,8 +234,20 @@ __device__ void tc_mma(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, u
   }
 }
 
+// phase timers of one CTA (development aid: -DDNBC_TC_TIMING prints clock64 totals of block 0)
+#ifdef DNBC_TC_TIMING
+#define TCT_DECL long long tct[6] = {0, 0, 0, 0, 0, 0}, tct0 = 0
+#define TCT_START tct0 = clock64()
+#define TCT_LAP(i) do { const long long n_ = clock64(); tct[i] += n_ - tct0; tct0 = n_; } while (0)
+#else
+#define TCT_DECL
+#define TCT_START
+#define TCT_LAP(i)
+#endif
+
 template <int DIR>   // 0 = forward, 1 = backward
 __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
+  TCT_DECL;
   extern __shared__ unsigned char smraw[];
   __shared__ __align__(8) unsigned long long bars[6];        // full[2], empty[2], done[2]
   __shared__ uint32_t tmem_slot;
@@ -179,6 +263,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
   const uint32_t smem_base = (smem_u32(smraw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[2]), bar_done = smem_u32(&bars[4]);
   const uint32_t my_done = bar_done + 8 * (col0 / TC_NH);    // the accumulator half this thread's columns are in
+  unsigned char *tb = smraw + (smem_base - smem_u32(smraw)) + 2 * STAGE_BYTES + (w & 7) * TB_BYTES;   // this warp's transpose tile
+  const int row0 = (w & 3) * 32;
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) mbar_init(bar_full + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -207,6 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
     __syncthreads();
     const int Tmax = sTmax;
     for (int k = 0; k < Tmax; ++k) {
+      TCT_START;
       if (!epi) {
         // ---- warp 8: producer, warp 9: MMA issuer (one elected lane each)
         if (k > 0 && lane == 0) {
@@ -228,13 +315,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
       if (DIR == 0) {
         // ---- v = d * exp(E - m); c = sum v; alpha = v / c ----
         float sum = 0.f;
+        if (vec) {
+          // coalesced path (tb_* helpers): emission chunks are fetched one chunk ahead
+          const unsigned lmask = __ballot_sync(0xffffffffu, live);
+          int pp[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
+          float4 en4[8];
+          chunk_ldg(a.E, pp, lmask, N, col0, lane, -INFINITY, en4);
+          if (live) {                                              // ... and the rest of the row is pulled into L2
+#pragma unroll 1
+            for (int c = col0 + 32; c < col0 + ncol; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
+          }
+          if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
+          TCT_LAP(0);
+          for (int ch = 0; ch < ncol / 32; ++ch) {
+            const int c0 = col0 + ch * 32;
+            float d[32], e[32];
+            chunk_to_rows(tb, lane, en4, e);
+            if (ch + 1 < ncol / 32) chunk_ldg(a.E, pp, lmask, N, c0 + 32, lane, -INFINITY, en4);
+            if (k > 0) tmem_ld32(trow + c0, d);
+            else load32(a.pi, c0, N, false, true, 0.f, d);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              d[i] *= ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E);
+              sum += d[i];
+            }
+            tmem_st32(trow + c0, d);
+          }
+          rsum[row][half] = sum;
+          TCT_LAP(1);
+          epi_sync();
+          TCT_LAP(2);
+          const float c = rsum[row][0] + rsum[row][1];
+          const float inv = live ? 1.0f / c : 0.f;
+          for (int ch = 0; ch < ncol / 32; ++ch) {
+            const int c0 = col0 + ch * 32;
+            float d[32];
+            tmem_ld32(trow + c0, d);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] *= inv;
+            rows_to_tb(tb, lane, d);
+            tb_store_f32(tb, a.AL, pp, lmask, N, c0, lane, 0);
+            tb_store_split(tb, xt, row0, c0, lane);
+            __syncwarp();
+          }
+          if (live && half == 0) {
+            a.cs[p] = c;
+            ll += (double)logf(c) + (double)mxs;
+          }
+        } else {
         float e[32], en[32];
         load32(Erow, col0, N, vec, live, -INFINITY, en);           // emission rows are fetched one chunk ahead
-        if (live && vec) {                                         // ... and the rest of the row is pulled into L2
-#pragma unroll 1
-          for (int c = col0 + 32; c < col0 + ncol; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
-        }
         if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
+        TCT_LAP(0);
         for (int ch = 0; ch < ncol / 32; ++ch) {
           const int c0 = col0 + ch * 32;
           float d[32];
@@ -251,7 +385,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           tmem_st32(trow + c0, d);
         }
         rsum[row][half] = sum;
+        TCT_LAP(1);
         epi_sync();
+        TCT_LAP(2);
         const float c = rsum[row][0] + rsum[row][1];
         const float inv = live ? 1.0f / c : 0.f;
         for (int ch = 0; ch < ncol / 32; ++ch) {
@@ -267,9 +403,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           a.cs[p] = c;
           ll += (double)logf(c) + (double)mxs;
         }
+        }
       } else {
         // ---- beta_t in TMEM (1 on the last step); gamma = alpha * beta; next u = exp(E_t - m_t) beta / c_t ----
         const float ic = live ? 1.0f / a.cs[p] : 0.f;
+        if (vec) {
+          // coalesced path (tb_* helpers)
+          const unsigned lmask = __ballot_sync(0xffffffffu, live);
+          const unsigned tpos = __ballot_sync(0xffffffffu, live && t > 0);
+          int pp[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
+          float4 qa[8], qe[8];
+          chunk_ldg(a.AL, pp, lmask, N, col0, lane, 0.f, qa);
+          if (live) {                                              // this step's alpha and emission rows -> L2
+#pragma unroll 1
+            for (int c = col0; c < col0 + ncol; c += 32) {
+              if (c > col0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.AL + p * N + c));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
+            }
+          }
+          if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
+          TCT_LAP(0);
+          // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
+          // ~1e-5 per step, so beta^_t is rescaled to make it 1 at every step (as k_fb2 / k_fb3 do)
+          float sdot = 0.f;
+          for (int ch = 0; ch < ncol / 32; ++ch) {
+            const int c0 = col0 + ch * 32;
+            float d[32], al[32];
+            chunk_to_rows(tb, lane, qa, al);
+            if (ch + 1 < ncol / 32) chunk_ldg(a.AL, pp, lmask, N, c0 + 32, lane, 0.f, qa);
+            if (k > 0) tmem_ld32(trow + c0, d);
+            else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d[i] = 1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sdot = fmaf(al[i], d[i], sdot);
+          }
+          rsum[row][half] = sdot;
+          TCT_LAP(1);
+          epi_sync();
+          TCT_LAP(2);
+          sdot = rsum[row][0] + rsum[row][1];
+          const float fix = (live && sdot > 0.f) ? 1.0f / sdot : 1.f;
+          for (int ch = 0; ch < ncol / 32; ++ch) {
+            const int c0 = col0 + ch * 32;
+            float d[32], e[32], al[32];
+            // (both rows were pulled into L2 at the top of the step; the TMEM load overlaps the fetch)
+            chunk_ldg(a.AL, pp, lmask, N, c0, lane, 0.f, qa);
+            chunk_ldg(a.E, pp, lmask, N, c0, lane, -INFINITY, qe);
+            if (k > 0) tmem_ld32(trow + c0, d);
+            else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d[i] = 1.f;
+            }
+            chunk_to_rows(tb, lane, qa, al);
+            chunk_to_rows(tb, lane, qe, e);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              d[i] *= fix;
+              al[i] *= d[i];                                                   // gamma
+              e[i] = (live && t > 0) ? ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E) * d[i] * ic : 0.f;   // next u
+            }
+            rows_to_tb(tb, lane, al);
+            tb_store_f32(tb, a.GA, pp, lmask, N, c0, lane, 0);
+            __syncwarp();
+            if (live && t == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (al[i] != 0.f) atomicAdd(a.stats + a.st_pi + c0 + i, (double)al[i]);
+            }
+            rows_to_tb(tb, lane, e);
+            tb_store_f32(tb, a.U, pp, tpos, N, c0, lane, -1);
+            if (k == 0) {                                                      // no transition out of the last step
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3);
+                if ((lmask >> rr) & 1u) *((float4 *)(a.U + (int64_t)pp[it] * N + c0) + (lane & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            tb_store_split(tb, xt, row0, c0, lane);
+            __syncwarp();
+          }
+        } else {
         if (live && vec) {                                         // this step's alpha and emission rows -> L2
 #pragma unroll 1
           for (int c = col0; c < col0 + ncol; c += 32) {
@@ -278,6 +495,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           }
         }
         if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
+        TCT_LAP(0);
         // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
         // ~1e-5 per step, so beta^_t is rescaled to make it 1 at every step (as k_fb2 / k_fb3 do)
         float fix = 1.f;
@@ -296,7 +514,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
             for (int i = 0; i < 32; ++i) s = fmaf(al[i], d[i], s);
           }
           rsum[row][half] = s;
+          TCT_LAP(1);
           epi_sync();
+          TCT_LAP(2);
           s = rsum[row][0] + rsum[row][1];
           fix = (live && s > 0.f) ? 1.0f / s : 1.f;
         }
@@ -334,18 +554,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           }
           store_split(e, xt, row, c0);
         }
+        }
       }
       // the staging tiles are read by the bulk copies (async proxy) of the next step
       asm volatile("fence.proxy.async.global;" ::: "memory");
+      TCT_LAP(3);
       }
       if (k > 0) gsteps += 1;
       // TMEM reads done and the staging tiles visible before the next step's MMAs / loads
       tc_fence_before();
       __threadfence();
+      TCT_LAP(4);
       __syncthreads();
+      TCT_LAP(5);
     }
   }
   if (epi && DIR == 0 && half == 0 && ll != 0.0) atomicAdd(a.stats, ll);
+#ifdef DNBC_TC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 128 || tid == 256 || tid == 288))
+    printf("k_fb_tc<%d> tid %3d: wait-done %lld  pass1 %lld  sync %lld  pass2 %lld  fence %lld  step-barrier %lld (clk)\n", DIR, tid,
+           tct[0], tct[1], tct[2], tct[3], tct[4], tct[5]);
+#endif
   tc_fence_before();
   __syncthreads();
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
@@ -419,7 +648,7 @@ int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bo
   StatsLayout sl = stats_layout(c->dm);
   TcArgs a{N, NP, c->d_off, s0, s1, p0, c->E, c->tc_mrow, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi, c->t_pi,
            backward ? t : t + 4 * n, (unsigned char *)c->tc_x};
-  const size_t smem = 2 * STAGE_BYTES + 1024;
+  const size_t smem = 2 * STAGE_BYTES + 1024 + (TC_EPI / 32) * TB_BYTES;   // ring + alignment slack + transpose tiles
   if (!backward) {
     c->launches++;
     k_rowmax<<<c->sm_count * 8, 256, 0, c->stream>>>(c->E, N, np, c->tc_mrow);
