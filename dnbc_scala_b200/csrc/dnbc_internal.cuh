@@ -168,6 +168,7 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np);
 bool fb3_supported(const dnbc_ctx *c);
 void launch_fb3(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 bool fb2_supported(const dnbc_ctx *c);
+bool fb2_fuses_xi(const dnbc_ctx *c);
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 bool viterbi_tile_supported(const dnbc_ctx *c);
 int launch_viterbi_tile(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path, double *score,

@@ -49,6 +49,7 @@ struct Fb2Args {
   float *cs;        // [np]    c_t
   double *stats;    // packed statistics ([0] = log-likelihood)
   int64_t st_pi;    // offset of the pi-stat
+  int64_t st_xi;    // offset of the xi-stat (transition statistics fused into the backward sweep, XI variants)
 };
 
 constexpr int FB_WARPS = 4;
@@ -86,6 +87,32 @@ __device__ __forceinline__ void matvec(const float *vec, const u64 (&M)[R][(NP +
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) out[r] = hsum2(part[r][0], part[r][1]);
+}
+
+// The same dot product for one matrix line, also accumulating this lane's row of the outer product
+// alpha^_t(i) u_{t+1}(j) (the transition statistics): the u pairs are already in registers, so the
+// statistics cost one more FFMA2 per pair instead of a separate pass over alpha^ and u (k_xi).
+template <int NP>
+__device__ __forceinline__ float matvec_xi(const float *vec, const u64 (&M)[(NP + 1) / 2], float al, u64 (&X)[(NP + 1) / 2]) {
+  const u64 al2 = pk(al, al);
+  u64 p0 = 0ull, p1 = 0ull;
+  if (NP % 4 == 0) {
+    const float4 *v4 = (const float4 *)vec;
+#pragma unroll
+    for (int i4 = 0; i4 < NP / 4; ++i4) {
+      const float4 v = v4[i4];
+      const u64 v01 = pk(v.x, v.y), v23 = pk(v.z, v.w);
+      p0 = fma2(v01, M[2 * i4], p0);
+      p1 = fma2(v23, M[2 * i4 + 1], p1);
+      X[2 * i4] = fma2(v01, al2, X[2 * i4]);
+      X[2 * i4 + 1] = fma2(v23, al2, X[2 * i4 + 1]);
+    }
+  } else {                                                   // NP == 2
+    const float2 v = *(const float2 *)vec;
+    p0 = fma2(pk(v.x, v.y), M[0], p0);
+    X[0] = fma2(pk(v.x, v.y), al2, X[0]);
+  }
+  return hsum2(p0, p1);
 }
 
 // ---- forward: alpha^_t(j) = b~_t(j) sum_i alpha^_{t-1}(i) a_ij / c_t ;  LL += ln c_t + m_t
@@ -199,8 +226,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
 
 // ---- backward: beta^_t(i) = sum_j a_ij u_t(j),  u_t(j) = b~_{t+1}(j) beta^_{t+1}(j) / c_{t+1};
 //      gamma_t = alpha^_t beta^_t;  pi-stat += gamma_0
-template <int LG, int R, int SQ>
+//      XI (R == 1 only): xi-stat[i][j] += a_ij sum_t alpha^_t(i) u_{t+1}(j) accumulated in registers (fp32
+//      over windows of ~4096 points, flushed with fp64 atomics); u is then not written to HBM at all
+template <int LG, int R, int SQ, bool XI>
 __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
+  static_assert(!XI || R == 1, "fused transition statistics need the whole row in one register line");
   constexpr int NP = LG * R, PG = 32 / LG;
   __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
   const int N = a.dm.N, Npad = a.dm.Npad;
@@ -209,6 +239,26 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
   u64 Arow[R][(NP + 1) / 2];
   int ir[R];
   double piacc[R];
+  u64 xacc[XI ? (NP + 1) / 2 : 1];
+  int xcount = 0;
+#pragma unroll
+  for (int jj = 0; jj < (XI ? (NP + 1) / 2 : 1); ++jj) xacc[jj] = 0ull;
+  auto xi_flush = [&]() {
+    if constexpr (XI) {
+#pragma unroll
+      for (int jj = 0; jj < (XI ? (NP + 1) / 2 : 1); ++jj) {
+        float x0, x1, a0, a1;
+        unpk(xacc[jj], x0, x1);
+        unpk(Arow[0][jj], a0, a1);
+        if (ir[0] < N && 2 * jj < N && x0 != 0.f)
+          atomicAdd(a.stats + a.st_xi + (int64_t)ir[0] * N + 2 * jj, (double)x0 * (double)a0);
+        if (ir[0] < N && 2 * jj + 1 < N && x1 != 0.f)
+          atomicAdd(a.stats + a.st_xi + (int64_t)ir[0] * N + 2 * jj + 1, (double)x1 * (double)a1);
+        xacc[jj] = 0ull;
+      }
+      xcount = 0;
+    }
+  };
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     ir[r] = lj + LG * r;
@@ -274,15 +324,18 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const float u = ex2_approx((e[q][r] - m[q]) * (float)DNBC_LOG2E) * beta[q][r] * ic;
-            if (t >= 0 && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = u;
-            sv[w][gi][q][ir[r]] = u;
+            if (!XI && t >= 0 && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = u;
+            sv[w][gi][q][ir[r]] = (XI && t < 0) ? 0.f : u;
           }
         }
         __syncwarp(mask);
 #pragma unroll
-        for (int q = 0; q < SQ; ++q) matvec<NP, R>(sv[w][gi][q], Arow, beta[q]);
+        for (int q = 0; q < SQ; ++q) {
+          if constexpr (XI) beta[q][0] = matvec_xi<NP>(sv[w][gi][q], Arow[0], al[q][0], xacc);
+          else matvec<NP, R>(sv[w][gi][q], Arow, beta[q]);
+        }
         __syncwarp(mask);
-      } else {
+      } else if (!XI) {
 #pragma unroll
         for (int q = 0; q < SQ; ++q) {
           const int t = T[q] - 1;
@@ -317,7 +370,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
         }
       }
     }
+    xcount += Tmax * SQ;
+    if (XI && xcount >= 4096) xi_flush();
   }
+  xi_flush();
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if (ir[r] < N && piacc[r] != 0.0) atomicAdd(a.stats + a.st_pi + ir[r], piacc[r]);
@@ -332,15 +388,21 @@ static void launch_fb2_t(dnbc_ctx *c, const Fb2Args &a, bool backward) {
   const int64_t cap = (int64_t)c->sm_count * (LG * R > 32 ? 2 : 4);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (backward) k_backward2<LG, R, SQ><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
-  else k_forward2<LG, R, SQ><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
+  if (!backward) k_forward2<LG, R, SQ><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
+  else if (R == 1 && fb2_fuses_xi(c)) k_backward2<LG, R, SQ, R == 1><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
+  else k_backward2<LG, R, SQ, false><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
 }
 
 bool fb2_supported(const dnbc_ctx *c) { return c->dm.Npad <= 64; }
+// up to 32 states the backward sweep accumulates the transition statistics itself (launch_xi is then a no-op)
+bool fb2_fuses_xi(const dnbc_ctx *c) {
+  static const bool off = getenv("DNBC_NO_XI_FUSE") != nullptr;
+  return !off && !fb3_supported(c) && fb2_supported(c) && c->dm.Npad <= 32;
+}
 
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) {
   StatsLayout sl = stats_layout(c->dm);
-  Fb2Args a{c->dm, c->tables(), c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi};
+  Fb2Args a{c->dm, c->tables(), c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi, sl.xi};
   switch (c->dm.Npad) {
     case 1:
     case 2: launch_fb2_t<2, 1>(c, a, backward); break;

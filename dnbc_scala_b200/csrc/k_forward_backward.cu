@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(256) k_xi(int N, int Npad, const float *__rest
 
 void launch_xi(dnbc_ctx *c, int64_t np) {
   if (np <= 0) return;
+  if (fb2_fuses_xi(c)) return;                               // accumulated inside k_backward2 (k_fb2.cu)
   FamTimer ft(c, FAM_XI);
   if (xi_tc_supported(c)) {                                  // N >= 64: tcgen05 GEMM (k_xi_tc.cu)
     launch_xi_tc(c, np);

@@ -462,7 +462,8 @@ __device__ __forceinline__ bool stat_stage2(StatRegs<KP> &q, const StatPend<KP> 
 // FULL: all 32 points exist and the lane's state is real, so the posterior fetches carry no predicates.
 template <int KP, bool HAS_C, bool HAS_D, bool GSUM, bool FULL>
 __device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *bd, const float *gp, int gstep, float xreg,
-                                           int vreg, int LG, int PG, int lp, int base, int pe, bool jon) {
+                                           int vreg, int NS, int PG, int lp, int base, int pe, bool jon) {
+  // NS = steps of PG points that cover the block's 32 points (= the lane-group size when that divides 32)
   constexpr bool fast = FULL;
   float gn[SPB];
   float gsl = 0.f;   // gamma sum of this block; folded into fp64 per block (an fp32 running sum over a
@@ -477,22 +478,22 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *b
     } else {
 #pragma unroll
       for (int i = 0; i < SPB; ++i)
-        gn[i] = (blk + i < LG && base + (blk + i) * PG + lp < pe && jon) ? __ldg(gp + i * gstep) : 0.f;
+        gn[i] = (blk + i < NS && (blk + i) * PG + lp < 32 && base + (blk + i) * PG + lp < pe && jon) ? __ldg(gp + i * gstep) : 0.f;
     }
     gp += SPB * gstep;
   };
   fetch(0);
   if (HAS_C && DNBC_STATS_PIPE) stat_stage1<KP>(q, __shfl_sync(0xffffffffu, xreg, lp), gn[0], pend[0]);
 #pragma unroll STATS_UNROLL
-  for (int blk = 0; blk < LG; blk += SPB) {                 // LG steps of PG points cover the 32 points
+  for (int blk = 0; blk < NS; blk += SPB) {                 // NS steps of PG points cover the 32 points
     float g[SPB];
 #pragma unroll
     for (int i = 0; i < SPB; ++i) g[i] = gn[i];
-    const bool more = blk + SPB < LG;
+    const bool more = blk + SPB < NS;
     if (more) fetch(blk + SPB);
 #pragma unroll
     for (int i = 0; i < SPB; ++i) {
-      const int qp = (blk + i) * PG + lp;                    // (steps past LG read lane qp & 31: g is 0 there)
+      const int qp = (blk + i) * PG + lp;                    // (steps past the block read lane qp & 31: g is 0 there)
       if (HAS_C) {
         if (DNBC_STATS_PIPE) {
           // stage 1 of the next point rides with stage 2 of this one; two buffers alternate (no copies)
@@ -520,8 +521,8 @@ __device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *b
     // block through the shifted evaluation, each lane contributing only where its fast path gave up
     // (the test below repeats stat_point_fast's: same inputs, same instructions, same outcome).
 #pragma unroll 1
-    for (int st = 0; st < LG; ++st) {
-      const bool on = jon && (fast || base + st * PG + lp < pe);
+    for (int st = 0; st < NS; ++st) {
+      const bool on = jon && (fast || (st * PG + lp < 32 && base + st * PG + lp < pe));
       const float g = on ? __ldg(gp0 + (int64_t)st * gstep) : 0.f;
       const float x = __shfl_sync(0xffffffffu, xreg, st * PG + lp);
       StatRegs<KP> probe = q;
@@ -539,11 +540,12 @@ template <int KP>
 __global__ void __launch_bounds__(DNBC_STATS_NW * 32, DNBC_STATS_OCC) k_stats_pk(StatArgs a) {
   extern __shared__ float bins[];                           // [warps of this CTA][Vmax+1][32]
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
-  const int LG = a.LG, PG = 32 / LG, NW = a.NW;
+  const int LG = a.LG, PG = 32 / LG, NS = (32 + PG - 1) / PG, NW = a.NW;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, lj = lane % LG, lp = lane / LG;
   const int j = blockIdx.y * 32 + lj;
   const int u = blockIdx.z * NW + w;                        // this warp's variable index
-  const bool has_c = u < C, has_d = u < D, jon = j < N;
+  // (a lane group that does not divide 32 leaves 32 - PG * LG idle lanes at the top of the warp)
+  const bool has_c = u < C, has_d = u < D, jon = j < N && lp < PG;
   const int bin_d = (Vmax + 1) * 32;
   float *bd = bins + (size_t)w * bin_d + lane;
   for (int t = 0; t <= Vmax; ++t) bd[t * 32] = 0.f;
@@ -594,11 +596,11 @@ __global__ void __launch_bounds__(DNBC_STATS_NW * 32, DNBC_STATS_OCC) k_stats_pk
     const float *gp = gcol + (int64_t)(base + lp) * N;      // posterior of this lane's state, step 0
     // warp-uniform: padded lanes (j >= N) run the same predicate-free path on state 0's posteriors and
     // their accumulators are never flushed (a per-lane flag made the warp execute BOTH block variants)
-    const bool fast = full && LG >= SPB;
+    const bool fast = full && LG >= SPB && PG * LG == 32;
 #define STAT_BLOCK(C_, D_, G_)                                                                          \
   do {                                                                                                 \
-    if (fast) stat_block<KP, C_, D_, G_, true>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, base, pe, jon);   \
-    else stat_block<KP, C_, D_, G_, false>(q, gs, bd, gp, gstep, xreg, vreg, LG, PG, lp, base, pe, jon);       \
+    if (fast) stat_block<KP, C_, D_, G_, true>(q, gs, bd, gp, gstep, xreg, vreg, NS, PG, lp, base, pe, jon);   \
+    else stat_block<KP, C_, D_, G_, false>(q, gs, bd, gp, gstep, xreg, vreg, NS, PG, lp, base, pe, jon);       \
   } while (0)
     if (has_c && has_d) { if (u == 0) STAT_BLOCK(true, true, true); else STAT_BLOCK(true, true, false); }
     else if (has_c) { if (u == 0) STAT_BLOCK(true, false, true); else STAT_BLOCK(true, false, false); }
@@ -691,7 +693,12 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   const Dims &d = c->dm;
   const int KP = (d.Kmax + 1) / 2;
   const int vec = (c->P % 4 == 0) && (p0 % 4 == 0);
-  EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, d.Npad < 32 ? d.Npad : 32, vec};
+  // lane group = the state count itself when it is below 32 (N = 10: three points x 10 states fill 30 lanes;
+  // the power-of-two group of 16 would fill 20).  Lanes past the last whole group repeat the first points of
+  // the next group and store the same values.
+  static const bool pow2lg = getenv("DNBC_EMIT_POW2") != nullptr;
+  const int LG = d.N >= 32 ? 32 : (pow2lg ? d.Npad : d.N);
+  EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, LG, vec};
   const size_t smem = emit_smem(d, KP);
   const int gy = (d.N + 31) / 32;                          // slices of 32 states that hold a real state
   int per_sm = (int)((200 * 1024) / (smem + 1024));
@@ -717,12 +724,13 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
   FamTimer ft(c, FAM_STATS_GMM);
   const Dims &d = c->dm;
   StatsLayout sl = stats_layout(d);
+  static const bool stats_pow2lg = getenv("DNBC_STATS_POW2") != nullptr;   // (A/B switch: power-of-two lane groups)
   int units = d.C > d.D ? d.C : d.D;
   if (units < 1) units = 1;
   const int NW = units > DNBC_STATS_NW ? DNBC_STATS_NW : units;
   const int gz = (units + NW - 1) / NW, gy = (d.N + 31) / 32;
   StatArgs a{d, c->tables(), c->data(), p0, (int)np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
-             c->d_stats + sl.gamma, d.Npad < 32 ? d.Npad : 32, NW, 4096};
+             c->d_stats + sl.gamma, d.N >= 32 ? 32 : (stats_pow2lg ? d.Npad : d.N), NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
   // 16 warps per SM (128 registers each): CTAs of NW warps, e.g. 3 x 5 warps when 5 variables
 #ifdef DNBC_STATS_PER_SM
