@@ -105,14 +105,17 @@ __device__ __forceinline__ void store32(float *g, int j0, int N, bool vec, const
 constexpr int TB_BYTES = 32 * 128;
 __device__ __forceinline__ uint32_t tb_off(int r, int c4) { return (uint32_t)(r * 128 + ((c4 ^ (r & 7)) << 4)); }
 
-// issue the loads of columns col .. col+31 of the warp's 32 rows (pp = point index of row it*4 + lane/8)
+// issue the loads of columns col .. col+31 of the warp's 32 rows (pp = point index of row it*4 + lane/8).
+// LAST: this is the last use of the lines (evict-first), so that the per-step streams (emissions, alpha,
+// gamma, u: ~150 MB per step over the chip) do not push the staging tiles and the transition matrix out of L2.
+template <bool LAST>
 __device__ __forceinline__ void chunk_ldg(const float *base, const int (&pp)[8], unsigned mask, int N, int col, int lane,
                                           float fill, float4 (&q)[8]) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + (lane >> 3);
-    q[it] = ((mask >> rr) & 1u) ? __ldg((const float4 *)(base + (int64_t)pp[it] * N + col) + (lane & 7))
-                                : make_float4(fill, fill, fill, fill);
+    const float4 *src = (const float4 *)(base + (int64_t)pp[it] * N + col) + (lane & 7);
+    q[it] = ((mask >> rr) & 1u) ? (LAST ? __ldcs(src) : __ldg(src)) : make_float4(fill, fill, fill, fill);
   }
 }
 // ... and hand every thread the 32 values of its own row
@@ -139,8 +142,8 @@ __device__ __forceinline__ void tb_store_f32(const unsigned char *tb, float *bas
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + (lane >> 3);
-    if ((mask >> rr) & 1u)
-      *((float4 *)(base + (int64_t)(pp[it] + drow) * N + col) + (lane & 7)) = *(const float4 *)(tb + tb_off(rr, lane & 7));
+    if ((mask >> rr) & 1u)                                   // streaming store: the consumers are later kernels
+      __stcs((float4 *)(base + (int64_t)(pp[it] + drow) * N + col) + (lane & 7), *(const float4 *)(tb + tb_off(rr, lane & 7)));
   }
 }
 // tile -> bf16 hi / lo split into the staging tile images (rows row0 .. row0+31, columns c0 .. c0+31 of X):
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
           float4 en4[8];
-          chunk_ldg(a.E, pp, lmask, N, col0, lane, -INFINITY, en4);
+          chunk_ldg<true>(a.E, pp, lmask, N, col0, lane, -INFINITY, en4);
           if (live) {                                              // ... and the rest of the row is pulled into L2
 #pragma unroll 1
             for (int c = col0 + 32; c < col0 + ncol; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
             const int c0 = col0 + ch * 32;
             float d[32], e[32];
             chunk_to_rows(tb, lane, en4, e);
-            if (ch + 1 < ncol / 32) chunk_ldg(a.E, pp, lmask, N, c0 + 32, lane, -INFINITY, en4);
+            if (ch + 1 < ncol / 32) chunk_ldg<true>(a.E, pp, lmask, N, c0 + 32, lane, -INFINITY, en4);
             if (k > 0) tmem_ld32(trow + c0, d);
             else load32(a.pi, c0, N, false, true, 0.f, d);
 #pragma unroll
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
           float4 qa[8], qe[8];
-          chunk_ldg(a.AL, pp, lmask, N, col0, lane, 0.f, qa);
+          chunk_ldg<false>(a.AL, pp, lmask, N, col0, lane, 0.f, qa);
           if (live) {                                              // this step's alpha and emission rows -> L2
 #pragma unroll 1
             for (int c = col0; c < col0 + ncol; c += 32) {
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
             const int c0 = col0 + ch * 32;
             float d[32], al[32];
             chunk_to_rows(tb, lane, qa, al);
-            if (ch + 1 < ncol / 32) chunk_ldg(a.AL, pp, lmask, N, c0 + 32, lane, 0.f, qa);
+            if (ch + 1 < ncol / 32) chunk_ldg<false>(a.AL, pp, lmask, N, c0 + 32, lane, 0.f, qa);
             if (k > 0) tmem_ld32(trow + c0, d);
             else {
 #pragma unroll
@@ -451,8 +454,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
             const int c0 = col0 + ch * 32;
             float d[32], e[32], al[32];
             // (both rows were pulled into L2 at the top of the step; the TMEM load overlaps the fetch)
-            chunk_ldg(a.AL, pp, lmask, N, c0, lane, 0.f, qa);
-            chunk_ldg(a.E, pp, lmask, N, c0, lane, -INFINITY, qe);
+            chunk_ldg<true>(a.AL, pp, lmask, N, c0, lane, 0.f, qa);
+            chunk_ldg<true>(a.E, pp, lmask, N, c0, lane, -INFINITY, qe);
             if (k > 0) tmem_ld32(trow + c0, d);
             else {
 #pragma unroll
