@@ -662,6 +662,15 @@ static size_t emit_smem(const Dims &d, int KP) {
   return (size_t)d.C * KP * 32 * (sizeof(float4) + sizeof(float2)) + (size_t)d.D * (d.Vmax + 1) * 32 * sizeof(float);
 }
 
+// Lanes per group of states in the emission / statistics sweeps.  Normally the padded (power-of-two) state
+// count, so that groups tile the warp; the exact state count when that puts more points into a warp
+// (N = 10: 3 x 10 lanes instead of 2 x 16; N = 5: 6 x 5 instead of 4 x 8).
+static int lane_group(const Dims &d, bool pow2_only) {
+  if (d.N >= 32) return 32;
+  const int pg_pad = 32 / (d.Npad < 32 ? d.Npad : 32), pg_exact = 32 / d.N;
+  return (!pow2_only && pg_exact > pg_pad) ? d.N : (d.Npad < 32 ? d.Npad : 32);
+}
+
 bool mixture_emission_fast(const dnbc_ctx *c) {
   const int KP = (c->dm.Kmax + 1) / 2;
   return KP <= 4 && c->dm.C <= 64 && emit_smem(c->dm, KP) <= 100 * 1024;
@@ -697,7 +706,7 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   // the power-of-two group of 16 would fill 20).  Lanes past the last whole group repeat the first points of
   // the next group and store the same values.
   static const bool pow2lg = getenv("DNBC_EMIT_POW2") != nullptr;
-  const int LG = d.N >= 32 ? 32 : (pow2lg ? d.Npad : d.N);
+  const int LG = lane_group(d, pow2lg);
   EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, LG, vec};
   const size_t smem = emit_smem(d, KP);
   const int gy = (d.N + 31) / 32;                          // slices of 32 states that hold a real state
@@ -730,7 +739,7 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
   const int NW = units > DNBC_STATS_NW ? DNBC_STATS_NW : units;
   const int gz = (units + NW - 1) / NW, gy = (d.N + 31) / 32;
   StatArgs a{d, c->tables(), c->data(), p0, (int)np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
-             c->d_stats + sl.gamma, d.N >= 32 ? 32 : (stats_pow2lg ? d.Npad : d.N), NW, 4096};
+             c->d_stats + sl.gamma, lane_group(d, stats_pow2lg), NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
   // 16 warps per SM (128 registers each): CTAs of NW warps, e.g. 3 x 5 warps when 5 variables
 #ifdef DNBC_STATS_PER_SM
