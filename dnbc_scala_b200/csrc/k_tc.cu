@@ -326,10 +326,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
           float4 en4[8];
           chunk_ldg<true>(a.E, pp, lmask, N, col0, lane, -INFINITY, en4);
-          if (live) {                                              // ... and the rest of the row is pulled into L2
-#pragma unroll 1
-            for (int c = col0 + 32; c < col0 + ncol; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
-          }
           if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
           TCT_LAP(0);
           for (int ch = 0; ch < ncol / 32; ++ch) {
@@ -419,13 +415,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
           float4 qa[8], qe[8];
           chunk_ldg<false>(a.AL, pp, lmask, N, col0, lane, 0.f, qa);
-          if (live) {                                              // this step's alpha and emission rows -> L2
-#pragma unroll 1
-            for (int c = col0; c < col0 + ncol; c += 32) {
-              if (c > col0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.AL + p * N + c));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
-            }
-          }
+          // (no L2 prefetch of the step's rows: ~190 MB stream through the 126 MB L2 per step, so lines fetched a
+          // product phase ahead were evicted again before their use -- measured 97 -> 94 ms without it)
           if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
           TCT_LAP(0);
           // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
@@ -472,10 +463,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
             rows_to_tb(tb, lane, al);
             tb_store_f32(tb, a.GA, pp, lmask, N, c0, lane, 0);
             __syncwarp();
-            if (live && t == 0) {
+            const unsigned t0mask = __ballot_sync(0xffffffffu, live && t == 0);
+            if (t0mask) {
+              // pi-stat += gamma_0: the rows at their first step go through the tile once more and each lane adds up
+              // one state column, so a warp issues 32 atomics instead of 32 x 32 (148 batches hitting 512 addresses)
+              const bool mine = live && t == 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (al[i] != 0.f) atomicAdd(a.stats + a.st_pi + c0 + i, (double)al[i]);
+              for (int i = 0; i < 32; ++i) al[i] = mine ? al[i] : 0.f;
+              rows_to_tb(tb, lane, al);
+              float colsum = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) colsum += *(const float *)(tb + tb_off(r, lane >> 2) + (lane & 3) * 4);
+              if (colsum != 0.f) atomicAdd(a.stats + a.st_pi + c0 + lane, (double)colsum);
+              __syncwarp();
             }
             rows_to_tb(tb, lane, e);
             tb_store_f32(tb, a.U, pp, tpos, N, c0, lane, -1);
@@ -490,13 +490,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
             __syncwarp();
           }
         } else {
-        if (live && vec) {                                         // this step's alpha and emission rows -> L2
-#pragma unroll 1
-          for (int c = col0; c < col0 + ncol; c += 32) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.AL + p * N + c));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Erow + c));
-          }
-        }
         if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
         TCT_LAP(0);
         // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
