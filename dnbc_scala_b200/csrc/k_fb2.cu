@@ -119,6 +119,7 @@ __device__ __forceinline__ float matvec_xi(const float *vec, const u64 (&M)[(NP 
 template <int LG, int R, int SQ>
 __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
   constexpr int NP = LG * R, PG = 32 / LG;
+  constexpr int PF = R == 1 ? 3 : 1;                        // emission rows in flight ahead of the step
   __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
   const int N = a.dm.N, Npad = a.dm.Npad;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
@@ -143,7 +144,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
   for (int64_t sb = a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
     int64_t row[SQ], pt[SQ];
     int T[SQ], Tmax = 0;
-    float alpha[SQ][R], en[SQ][R];
+    // Only the product alpha^_{t-1} A, the normaliser and the rescale sit on the step-to-step dependency chain:
+    // the emission factor b~_t = exp(E_t - max_j E_t) of the NEXT step is formed while this step's chain runs
+    // (its maximum rides in the same shuffle rounds as the normaliser), and the emission rows are requested PF
+    // steps ahead, so neither a load nor the second reduction is ever waited for.
+    float alpha[SQ][R], ering[PF][SQ][R], bcur[SQ][R], mcur[SQ];
 #pragma unroll
     for (int q = 0; q < SQ; ++q) {
       const int64_t s = sb + q;
@@ -151,31 +156,36 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
       pt[q] = s < a.s1 ? a.off[s] - a.p0 : 0;
       row[q] = pt[q] * N;
       Tmax = T[q] > Tmax ? T[q] : Tmax;
+    }
+    auto load_e = [&](int q, int r, int tt) -> float {
+      return (tt < T[q] && jr[r] < N) ? a.E[row[q] + (int64_t)tt * N + jr[r]] : -INFINITY;
+    };
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+      mcur[q] = -INFINITY;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         alpha[q][r] = 0.f;
-        en[q][r] = (T[q] > 0 && jr[r] < N) ? a.E[row[q] + jr[r]] : -INFINITY;
+        bcur[q][r] = load_e(q, r, 0);
+        mcur[q] = fmaxf(mcur[q], bcur[q][r]);
+#pragma unroll
+        for (int i = 0; i < PF; ++i) ering[i][q][r] = load_e(q, r, 1 + i);
       }
+    }
+#pragma unroll
+    for (int o = LG / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) mcur[q] = fmaxf(mcur[q], __shfl_xor_sync(mask, mcur[q], o, LG));
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+      if (mcur[q] == -INFINITY) mcur[q] = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) bcur[q][r] = ex2_approx((bcur[q][r] - mcur[q]) * (float)DNBC_LOG2E);
     }
     for (int t = 0; t < Tmax; ++t) {
       // phases run over all SQ sequences so their dependency chains interleave; only the two
       // __syncwarp()s around the shared-memory exchange order the instruction stream
-      float e[SQ][R], m[SQ], acc[SQ][R], csum[SQ];
-#pragma unroll
-      for (int q = 0; q < SQ; ++q) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          e[q][r] = en[q][r];
-          en[q][r] = (t + 1 < T[q] && jr[r] < N) ? a.E[row[q] + (int64_t)(t + 1) * N + jr[r]] : -INFINITY;
-        }
-        m[q] = e[q][0];
-#pragma unroll
-        for (int r = 1; r < R; ++r) m[q] = fmaxf(m[q], e[q][r]);
-      }
-#pragma unroll
-      for (int o = LG / 2; o > 0; o >>= 1)
-#pragma unroll
-        for (int q = 0; q < SQ; ++q) m[q] = fmaxf(m[q], __shfl_xor_sync(mask, m[q], o, LG));
+      float acc[SQ][R], csum[SQ], mnext[SQ];
       if (t == 0) {
 #pragma unroll
         for (int q = 0; q < SQ; ++q)
@@ -193,18 +203,22 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
       }
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
-        if (m[q] == -INFINITY) m[q] = 0.f;
         csum[q] = 0.f;
+        mnext[q] = ering[0][q][0];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          acc[q][r] *= ex2_approx((e[q][r] - m[q]) * (float)DNBC_LOG2E);
+          acc[q][r] *= bcur[q][r];
           csum[q] += acc[q][r];
+          mnext[q] = fmaxf(mnext[q], ering[0][q][r]);
         }
       }
 #pragma unroll
       for (int o = LG / 2; o > 0; o >>= 1)
 #pragma unroll
-        for (int q = 0; q < SQ; ++q) csum[q] += __shfl_xor_sync(mask, csum[q], o, LG);
+        for (int q = 0; q < SQ; ++q) {
+          csum[q] += __shfl_xor_sync(mask, csum[q], o, LG);
+          mnext[q] = fmaxf(mnext[q], __shfl_xor_sync(mask, mnext[q], o, LG));
+        }
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         const bool live = t < T[q];
@@ -216,7 +230,16 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
         }
         if (live && lj == 0) {
           a.cs[pt[q] + t] = csum[q];
-          ll += (double)(lg2_approx(csum[q]) * (float)DNBC_LN2) + (double)m[q];
+          ll += (double)(lg2_approx(csum[q]) * (float)DNBC_LN2) + (double)mcur[q];
+        }
+        // next step's emission factor; the ring moves up and its tail is requested
+        mcur[q] = mnext[q] == -INFINITY ? 0.f : mnext[q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          bcur[q][r] = ex2_approx((ering[0][q][r] - mcur[q]) * (float)DNBC_LOG2E);
+#pragma unroll
+          for (int i = 0; i + 1 < PF; ++i) ering[i][q][r] = ering[i + 1][q][r];
+          ering[PF - 1][q][r] = load_e(q, r, t + 1 + PF);
         }
       }
     }
@@ -232,6 +255,7 @@ template <int LG, int R, int SQ, bool XI>
 __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
   static_assert(!XI || R == 1, "fused transition statistics need the whole row in one register line");
   constexpr int NP = LG * R, PG = 32 / LG;
+  constexpr int PF = R == 1 ? 3 : 1;                        // rows in flight ahead of the step
   __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
   const int N = a.dm.N, Npad = a.dm.Npad;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
@@ -275,7 +299,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
   for (int64_t sb = a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
     int64_t row[SQ], pt[SQ];
     int T[SQ], Tmax = 0;
-    float beta[SQ][R], aln[SQ][R], en[SQ][R], csn[SQ];
+    // As in the forward sweep, only u = bu * beta, the product A u, the alpha.beta dot product and the rescale sit
+    // on the dependency chain: bu = exp(E_{t+1} - max) / c_{t+1} of the NEXT iteration is formed while this one
+    // runs (its maximum shares the shuffle rounds of the dot product) and alpha^ / E / c rows are requested PF
+    // iterations ahead.  Iteration k works at t = T - 1 - k and needs alpha^_t, E_{t+1}, c_{t+1}.
+    float beta[SQ][R], alr[PF][SQ][R], ering[PF][SQ][R], cring[PF][SQ], bu[SQ][R];
 #pragma unroll
     for (int q = 0; q < SQ; ++q) {
       const int64_t s = sb + q;
@@ -283,47 +311,43 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
       pt[q] = s < a.s1 ? a.off[s] - a.p0 : 0;
       row[q] = pt[q] * N;
       Tmax = T[q] > Tmax ? T[q] : Tmax;
-      csn[q] = 1.f;
+    }
+    auto load_al = [&](int q, int r, int tt) -> float {
+      return (tt >= 0 && ir[r] < N) ? a.AL[row[q] + (int64_t)tt * N + ir[r]] : 0.f;
+    };
+    auto load_e = [&](int q, int r, int tt) -> float {       // E_tt as the "t+1" quantity of step tt-1
+      return (tt >= 1 && ir[r] < N) ? a.E[row[q] + (int64_t)tt * N + ir[r]] : -INFINITY;
+    };
+    auto load_c = [&](int q, int tt) -> float { return tt >= 1 ? a.cs[pt[q] + tt] : 1.f; };
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+#pragma unroll
+      for (int i = 0; i < PF; ++i) cring[i][q] = load_c(q, T[q] - 1 - i);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         beta[q][r] = 1.f;
-        aln[q][r] = (T[q] > 0 && ir[r] < N) ? a.AL[row[q] + (int64_t)(T[q] - 1) * N + ir[r]] : 0.f;
-        en[q][r] = -INFINITY;
+        bu[q][r] = 0.f;
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          alr[i][q][r] = load_al(q, r, T[q] - 1 - i);
+          ering[i][q][r] = load_e(q, r, T[q] - 1 - i);
+        }
       }
     }
     // sequences of a pair are aligned at their LAST step: step index k counts back from it
     for (int k = 0; k < Tmax; ++k) {
-      float al[SQ][R], e[SQ][R], m[SQ], cn[SQ];
+      float al[SQ][R], mnext[SQ];
 #pragma unroll
-      for (int q = 0; q < SQ; ++q) {
-        const int t = T[q] - 1 - k;
-        cn[q] = csn[q];
+      for (int q = 0; q < SQ; ++q)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          al[q][r] = aln[q][r];
-          e[q][r] = en[q][r];
-          // prefetch for step t-1: alpha_{t-1}, and E_t / c_t (the "t+1" quantities of step t-1)
-          aln[q][r] = (t > 0 && ir[r] < N) ? a.AL[row[q] + (int64_t)(t - 1) * N + ir[r]] : 0.f;
-          en[q][r] = (t > 0 && ir[r] < N) ? a.E[row[q] + (int64_t)t * N + ir[r]] : -INFINITY;
-        }
-        csn[q] = t > 0 ? a.cs[pt[q] + t] : 1.f;
-        m[q] = e[q][0];
-#pragma unroll
-        for (int r = 1; r < R; ++r) m[q] = fmaxf(m[q], e[q][r]);
-      }
+        for (int r = 0; r < R; ++r) al[q][r] = alr[0][q][r];
       if (k > 0) {
-#pragma unroll
-        for (int o = LG / 2; o > 0; o >>= 1)
-#pragma unroll
-          for (int q = 0; q < SQ; ++q) m[q] = fmaxf(m[q], __shfl_xor_sync(mask, m[q], o, LG));
 #pragma unroll
         for (int q = 0; q < SQ; ++q) {
           const int t = T[q] - 1 - k;
-          if (m[q] == -INFINITY) m[q] = 0.f;
-          const float ic = rcp_approx(cn[q]);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const float u = ex2_approx((e[q][r] - m[q]) * (float)DNBC_LOG2E) * beta[q][r] * ic;
+            const float u = bu[q][r] * beta[q][r];
             if (!XI && t >= 0 && ir[r] < N) a.U[row[q] + (int64_t)t * N + ir[r]] = u;
             sv[w][gi][q][ir[r]] = (XI && t < 0) ? 0.f : u;
           }
@@ -350,13 +374,20 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         gsumq[q] = 0.f;
+        mnext[q] = ering[0][q][0];
 #pragma unroll
-        for (int r = 0; r < R; ++r) gsumq[q] = fmaf(al[q][r], beta[q][r], gsumq[q]);
+        for (int r = 0; r < R; ++r) {
+          gsumq[q] = fmaf(al[q][r], beta[q][r], gsumq[q]);
+          mnext[q] = fmaxf(mnext[q], ering[0][q][r]);
+        }
       }
 #pragma unroll
       for (int o = LG / 2; o > 0; o >>= 1)
 #pragma unroll
-        for (int q = 0; q < SQ; ++q) gsumq[q] += __shfl_xor_sync(mask, gsumq[q], o, LG);
+        for (int q = 0; q < SQ; ++q) {
+          gsumq[q] += __shfl_xor_sync(mask, gsumq[q], o, LG);
+          mnext[q] = fmaxf(mnext[q], __shfl_xor_sync(mask, mnext[q], o, LG));
+        }
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         const int t = T[q] - 1 - k;
@@ -367,6 +398,23 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
           const float g = al[q][r] * beta[q][r];
           if (t >= 0 && ir[r] < N) a.GA[row[q] + (int64_t)t * N + ir[r]] = g;
           if (t == 0) piacc[r] += (double)g;
+        }
+        // next iteration's factor (E_t, c_t are its "t+1" quantities); the rings move up, tails are requested
+        const float mn = mnext[q] == -INFINITY ? 0.f : mnext[q];
+        const float ic = rcp_approx(cring[0][q]);
+#pragma unroll
+        for (int i = 0; i + 1 < PF; ++i) cring[i][q] = cring[i + 1][q];
+        cring[PF - 1][q] = load_c(q, t - PF);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          bu[q][r] = ex2_approx((ering[0][q][r] - mn) * (float)DNBC_LOG2E) * ic;
+#pragma unroll
+          for (int i = 0; i + 1 < PF; ++i) {
+            ering[i][q][r] = ering[i + 1][q][r];
+            alr[i][q][r] = alr[i + 1][q][r];
+          }
+          ering[PF - 1][q][r] = load_e(q, r, t - PF);
+          alr[PF - 1][q][r] = load_al(q, r, t - PF);
         }
       }
     }
@@ -379,9 +427,9 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
     if (ir[r] < N && piacc[r] != 0.0) atomicAdd(a.stats + a.st_pi + ir[r], piacc[r]);
 }
 
-template <int LG, int R>
-static void launch_fb2_t(dnbc_ctx *c, const Fb2Args &a, bool backward) {
-  constexpr int SQ = 4, PG = 32 / LG;
+template <int LG, int R, int SQ>
+static void launch_fb2_sq(dnbc_ctx *c, const Fb2Args &a, bool backward) {
+  constexpr int PG = 32 / LG;
   const int64_t nseq = a.s1 - a.s0;
   const int64_t per_block = (int64_t)FB_WARPS * PG * SQ;
   int64_t blocks = (nseq + per_block - 1) / per_block;
@@ -391,6 +439,18 @@ static void launch_fb2_t(dnbc_ctx *c, const Fb2Args &a, bool backward) {
   if (!backward) k_forward2<LG, R, SQ><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
   else if (R == 1 && fb2_fuses_xi(c)) k_backward2<LG, R, SQ, R == 1><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
   else k_backward2<LG, R, SQ, false><<<(int)blocks, FB_WARPS * 32, 0, c->stream>>>(a);
+}
+
+// A lane group advances SQ = 4 sequences at a time so that their dependency chains interleave.  When the
+// whole chunk fits the GPU with one sequence per group (a README-sized data set: 1000 sequences), one
+// sequence per group is faster: the step time of a lone warp is its instruction count, not its chain.
+template <int LG, int R>
+static void launch_fb2_t(dnbc_ctx *c, const Fb2Args &a, bool backward) {
+  constexpr int PG = 32 / LG;
+  const int64_t one_wave = (int64_t)c->sm_count * (LG * R > 32 ? 2 : 4) * FB_WARPS * PG;
+  const char *force = getenv("DNBC_FB2_SQ");                // test hook: "4" keeps the interleaved variant on small inputs
+  if (R == 1 && a.s1 - a.s0 <= one_wave && !(force && force[0] == '4')) launch_fb2_sq<LG, R, 1>(c, a, backward);
+  else launch_fb2_sq<LG, R, 4>(c, a, backward);
 }
 
 bool fb2_supported(const dnbc_ctx *c) { return c->dm.Npad <= 64; }

@@ -305,6 +305,37 @@ def test_every_state_count_dispatch_path_matches_oracle(oracle, N):
     np.testing.assert_allclose(s32, oscore, rtol=1e-5)
 
 
+@pytest.mark.parametrize("N", [2, 3, 5, 10, 12, 17, 32])
+def test_register_resident_recursions_four_sequences_per_group(oracle, monkeypatch, N):
+    """k_fb2.cu advances one sequence per lane group on small inputs and four interleaved ones on large
+    inputs (DNBC_FB2_SQ=4 forces the latter here), and up to 32 states its backward sweep accumulates the
+    transition statistics itself: both variants against the fp64 oracle, ragged lengths, every lane-group
+    size (2 .. 32 lanes), with the emission / statistics sweeps on exact (non power-of-two) lane groups."""
+    m = random_model(oracle, N, [4, 3], [2, 3], 900 + N, transitions_per_state=min(N, 6))
+    rng = np.random.default_rng(910 + N)
+    lengths = [int(x) for x in rng.integers(1, 60, 45)] + [1, 0, 75]
+    data = sample(oracle, m, lengths, 920 + N)
+    q = perturb(oracle, m, 930 + N)
+    want = oracle.estep(q, data)
+    sw = oracle.split_stats(q, want)
+    gw = oracle.posteriors(q, data)
+    for force in ("4", None):
+        if force:
+            monkeypatch.setenv("DNBC_FB2_SQ", force)
+        else:
+            monkeypatch.delenv("DNBC_FB2_SQ", raising=False)
+        with ctx_for(nat, q) as ctx:
+            upload(ctx, data, labels=False, dtype=np.float32)
+            ctx.em_estep()
+            sg = oracle.split_stats(q, ctx.em_get_stats())
+            g = ctx.em_posteriors()
+        assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+        for key in ("pi", "xi", "gamma", "cat"):
+            np.testing.assert_allclose(sg[key], sw[key], rtol=1e-4, atol=1e-4, err_msg=f"{key} (SQ {force})")
+        np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=1e-4, atol=1e-3, err_msg="gmm s0")
+        np.testing.assert_allclose(g, gw, atol=2e-5)
+
+
 def test_randomised_shapes_against_the_oracle():
     """tests/fuzz_parity.py: 60 seeded random shapes (1..300 states, 0..3 + 0..3 variables, mixtures of
     1..8 components, sparse transitions, ragged and empty sequences) -- E-step statistics, posteriors and
