@@ -460,11 +460,15 @@ __device__ __forceinline__ bool stat_stage2(StatRegs<KP> &q, const StatPend<KP> 
 // 32 points: the warp-uniform role flags are template parameters so the inner loop carries no
 // per-point branches.  Posteriors are fetched SPB points ahead (gn) of the ones being consumed.
 // FULL: all 32 points exist and the lane's state is real, so the posterior fetches carry no predicates.
-template <int KP, bool HAS_C, bool HAS_D, bool GSUM, bool FULL>
+// DEEP (only with FULL): posteriors are fetched 8 points ahead instead of 4.  With at most two component pairs a
+// point costs ~60 clk, so four points do not cover an L2 miss (N = 512, K = 3: -7 %); with four pairs the extra
+// registers cost more than the latency they hide.
+template <int KP, bool HAS_C, bool HAS_D, bool GSUM, bool FULL, bool DEEP = false>
 __device__ __forceinline__ void stat_block(StatRegs<KP> &q, double &gs, float *bd, const float *gp, int gstep, float xreg,
                                            int vreg, int NS, int PG, int lp, int base, int pe, bool jon) {
   // NS = steps of PG points that cover the block's 32 points (= the lane-group size when that divides 32)
   constexpr bool fast = FULL;
+  constexpr int SPB = DEEP ? 2 * ::SPB : ::SPB;
   float gn[SPB];
   float gsl = 0.f;   // gamma sum of this block; folded into fp64 per block (an fp32 running sum over a
                      // 4096-point window reaches ~64 and would drop every posterior below 4e-6)
@@ -597,9 +601,11 @@ __global__ void __launch_bounds__(DNBC_STATS_NW * 32, DNBC_STATS_OCC) k_stats_pk
     // warp-uniform: padded lanes (j >= N) run the same predicate-free path on state 0's posteriors and
     // their accumulators are never flushed (a per-lane flag made the warp execute BOTH block variants)
     const bool fast = full && LG >= SPB && PG * LG == 32;
+    const bool deep = KP <= 2 && LG == 32;
 #define STAT_BLOCK(C_, D_, G_)                                                                          \
   do {                                                                                                 \
-    if (fast) stat_block<KP, C_, D_, G_, true>(q, gs, bd, gp, gstep, xreg, vreg, NS, PG, lp, base, pe, jon);   \
+    if (fast && deep) stat_block<KP, C_, D_, G_, true, KP <= 2>(q, gs, bd, gp, gstep, xreg, vreg, NS, PG, lp, base, pe, jon); \
+    else if (fast) stat_block<KP, C_, D_, G_, true>(q, gs, bd, gp, gstep, xreg, vreg, NS, PG, lp, base, pe, jon);   \
     else stat_block<KP, C_, D_, G_, false>(q, gs, bd, gp, gstep, xreg, vreg, NS, PG, lp, base, pe, jon);       \
   } while (0)
     if (has_c && has_d) { if (u == 0) STAT_BLOCK(true, true, true); else STAT_BLOCK(true, true, false); }
