@@ -24,18 +24,75 @@ __device__ __forceinline__ unsigned gmask() {
   const unsigned lane = threadIdx.x & 31u;
   return ((1u << (LG & 31)) - 1u) << ((lane / LG) * LG);
 }
+// A lane group is LG consecutive lanes.  Normally LG is a power of two (an xor butterfly reduces in log2 LG rounds);
+// the state counts 3, 5, 6, 9, 10 get groups of exactly LG lanes instead, because that puts more sequences into a
+// warp (N = 10: 3 x 10 lanes instead of 2 x 16) -- their reductions run a tree to the group's first lane plus a
+// broadcast (one round more).  Lanes past the last whole group idle.
 template <int LG>
-__device__ __forceinline__ float gmax(float v, unsigned mask) {
+struct GroupRed {
+  static constexpr bool POW2 = (LG & (LG - 1)) == 0;
+  static constexpr int P = LG <= 1 ? 1 : LG <= 2 ? 2 : LG <= 4 ? 4 : LG <= 8 ? 8 : LG <= 16 ? 16 : 32;   // next power of two
+  // SQ sums (+) and SQ maxima reduced together over the group; every lane ends up with the results
+  template <int SQ>
+  static __device__ __forceinline__ void sum_max(float (&sm)[SQ], float (&mx)[SQ], unsigned mask, int lj, int base) {
+    if constexpr (POW2) {
 #pragma unroll
-  for (int o = LG / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, LG));
-  return v;
-}
-template <int LG>
-__device__ __forceinline__ float gsum(float v, unsigned mask) {
+      for (int o = LG / 2; o > 0; o >>= 1)
 #pragma unroll
-  for (int o = LG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, LG);
-  return v;
-}
+        for (int q = 0; q < SQ; ++q) {
+          sm[q] += __shfl_xor_sync(mask, sm[q], o, LG);
+          mx[q] = fmaxf(mx[q], __shfl_xor_sync(mask, mx[q], o, LG));
+        }
+      return;
+    }
+#pragma unroll
+    for (int o = P / 2; o > 0; o >>= 1) {
+      const int src = POW2 ? base + (lj ^ o) : base + (lj + o < LG ? lj + o : lj);
+      const bool take = POW2 || (lj < o && lj + o < LG);
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        const float ts = __shfl_sync(mask, sm[q], src), tm = __shfl_sync(mask, mx[q], src);
+        if (take) {
+          sm[q] += ts;
+          mx[q] = fmaxf(mx[q], tm);
+        }
+      }
+    }
+    if (!POW2) {
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        sm[q] = __shfl_sync(mask, sm[q], base);
+        mx[q] = __shfl_sync(mask, mx[q], base);
+      }
+    }
+  }
+  template <int SQ>
+  static __device__ __forceinline__ void max_only(float (&mx)[SQ], unsigned mask, int lj, int base) {
+    if constexpr (POW2) {
+#pragma unroll
+      for (int o = LG / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) mx[q] = fmaxf(mx[q], __shfl_xor_sync(mask, mx[q], o, LG));
+      return;
+    }
+#pragma unroll
+    for (int o = P / 2; o > 0; o >>= 1) {
+      const int src = POW2 ? base + (lj ^ o) : base + (lj + o < LG ? lj + o : lj);
+      const bool take = POW2 || (lj < o && lj + o < LG);
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        const float tm = __shfl_sync(mask, mx[q], src);
+        if (take) mx[q] = fmaxf(mx[q], tm);
+      }
+    }
+    if (!POW2) {
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) mx[q] = __shfl_sync(mask, mx[q], base);
+    }
+  }
+};
+// length of the exchanged vector: the states of a group, padded to whole float4's (pad entries stay zero)
+__host__ __device__ constexpr int fb2_np(int LG, int R) { return LG * R <= 2 ? LG * R : (LG * R + 3) / 4 * 4; }
 
 struct Fb2Args {
   Dims dm;
@@ -117,13 +174,23 @@ __device__ __forceinline__ float matvec_xi(const float *vec, const u64 (&M)[(NP 
 
 // ---- forward: alpha^_t(j) = b~_t(j) sum_i alpha^_{t-1}(i) a_ij / c_t ;  LL += ln c_t + m_t
 template <int LG, int R, int SQ>
-__global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
-  constexpr int NP = LG * R, PG = 32 / LG;
+__global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_forward2(Fb2Args a) {
+  constexpr int NP = fb2_np(LG, R), PG = 32 / LG;
   constexpr int PF = R == 1 ? 3 : 1;                        // emission rows in flight ahead of the step
   __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
   const int N = a.dm.N, Npad = a.dm.Npad;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
   const unsigned mask = gmask<LG>();
+  const int base = gi * LG;                                  // first lane of this group
+  const bool idle = (32 % LG != 0) && gi >= PG;              // lanes past the last whole group (LG does not divide 32)
+  if constexpr ((NP < 4 ? 4 : NP) > LG * R) {                // pad entries of the exchanged vectors stay zero
+    if (!idle) {
+#pragma unroll
+      for (int q = 0; q < SQ; ++q)
+        for (int i = LG * R + lj; i < (NP < 4 ? 4 : NP); i += LG) sv[w][gi][q][i] = 0.f;
+    }
+    __syncwarp(mask);
+  }
   u64 Acol[R][(NP + 1) / 2];
   float pi[R];
   int jr[R];
@@ -141,7 +208,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
   const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;
   const int64_t gid = ((int64_t)blockIdx.x * FB_WARPS + w) * PG + gi;
   double ll = 0.0;
-  for (int64_t sb = a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
+  for (int64_t sb = idle ? a.s1 : a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
     int64_t row[SQ], pt[SQ];
     int T[SQ], Tmax = 0;
     // Only the product alpha^_{t-1} A, the normaliser and the rescale sit on the step-to-step dependency chain:
@@ -172,10 +239,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
         for (int i = 0; i < PF; ++i) ering[i][q][r] = load_e(q, r, 1 + i);
       }
     }
-#pragma unroll
-    for (int o = LG / 2; o > 0; o >>= 1)
-#pragma unroll
-      for (int q = 0; q < SQ; ++q) mcur[q] = fmaxf(mcur[q], __shfl_xor_sync(mask, mcur[q], o, LG));
+    GroupRed<LG>::template max_only<SQ>(mcur, mask, lj, base);
 #pragma unroll
     for (int q = 0; q < SQ; ++q) {
       if (mcur[q] == -INFINITY) mcur[q] = 0.f;
@@ -212,13 +276,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
           mnext[q] = fmaxf(mnext[q], ering[0][q][r]);
         }
       }
-#pragma unroll
-      for (int o = LG / 2; o > 0; o >>= 1)
-#pragma unroll
-        for (int q = 0; q < SQ; ++q) {
-          csum[q] += __shfl_xor_sync(mask, csum[q], o, LG);
-          mnext[q] = fmaxf(mnext[q], __shfl_xor_sync(mask, mnext[q], o, LG));
-        }
+      GroupRed<LG>::template sum_max<SQ>(csum, mnext, mask, lj, base);
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         const bool live = t < T[q];
@@ -252,14 +310,24 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_forward2(Fb2Args a) {
 //      XI (R == 1 only): xi-stat[i][j] += a_ij sum_t alpha^_t(i) u_{t+1}(j) accumulated in registers (fp32
 //      over windows of ~4096 points, flushed with fp64 atomics); u is then not written to HBM at all
 template <int LG, int R, int SQ, bool XI>
-__global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
+__global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_backward2(Fb2Args a) {
   static_assert(!XI || R == 1, "fused transition statistics need the whole row in one register line");
-  constexpr int NP = LG * R, PG = 32 / LG;
+  constexpr int NP = fb2_np(LG, R), PG = 32 / LG;
   constexpr int PF = R == 1 ? 3 : 1;                        // rows in flight ahead of the step
   __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
   const int N = a.dm.N, Npad = a.dm.Npad;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
   const unsigned mask = gmask<LG>();
+  const int base = gi * LG;                                  // first lane of this group
+  const bool idle = (32 % LG != 0) && gi >= PG;              // lanes past the last whole group (LG does not divide 32)
+  if constexpr ((NP < 4 ? 4 : NP) > LG * R) {                // pad entries of the exchanged vectors stay zero
+    if (!idle) {
+#pragma unroll
+      for (int q = 0; q < SQ; ++q)
+        for (int i = LG * R + lj; i < (NP < 4 ? 4 : NP); i += LG) sv[w][gi][q][i] = 0.f;
+    }
+    __syncwarp(mask);
+  }
   u64 Arow[R][(NP + 1) / 2];
   int ir[R];
   double piacc[R];
@@ -296,7 +364,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
   }
   const int64_t ngroups = (int64_t)gridDim.x * FB_WARPS * PG;
   const int64_t gid = ((int64_t)blockIdx.x * FB_WARPS + w) * PG + gi;
-  for (int64_t sb = a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
+  for (int64_t sb = idle ? a.s1 : a.s0 + gid * SQ; sb < a.s1; sb += ngroups * SQ) {
     int64_t row[SQ], pt[SQ];
     int T[SQ], Tmax = 0;
     // As in the forward sweep, only u = bu * beta, the product A u, the alpha.beta dot product and the rescale sit
@@ -381,13 +449,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_backward2(Fb2Args a) {
           mnext[q] = fmaxf(mnext[q], ering[0][q][r]);
         }
       }
-#pragma unroll
-      for (int o = LG / 2; o > 0; o >>= 1)
-#pragma unroll
-        for (int q = 0; q < SQ; ++q) {
-          gsumq[q] += __shfl_xor_sync(mask, gsumq[q], o, LG);
-          mnext[q] = fmaxf(mnext[q], __shfl_xor_sync(mask, mnext[q], o, LG));
-        }
+      GroupRed<LG>::template sum_max<SQ>(gsumq, mnext, mask, lj, base);
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         const int t = T[q] - 1 - k;
@@ -463,11 +525,26 @@ bool fb2_fuses_xi(const dnbc_ctx *c) {
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) {
   StatsLayout sl = stats_layout(c->dm);
   Fb2Args a{c->dm, c->tables(), c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi, sl.xi};
-  switch (c->dm.Npad) {
+  // lanes per group: the padded state count, or the exact one where that puts more sequences into a warp
+  // (the rule of lane_group() in k_mixture.cu: N = 3, 5, 6, 9, 10)
+  static const bool pow2 = getenv("DNBC_FB2_POW2") != nullptr;          // A/B switch
+  const int N = c->dm.N, Npad = c->dm.Npad;
+  // (a chunk that fits one wave of power-of-two groups is latency-bound: the exact groups' extra shuffle round
+  // would only lengthen its chain)
+  const int lgp = Npad < 32 ? Npad : 32;
+  const char *force = getenv("DNBC_FB2_SQ");                // test hook "4": the large-input kernels on small inputs
+  const bool one_wave = s1 - s0 <= (int64_t)c->sm_count * 4 * FB_WARPS * (32 / lgp) && !(force && force[0] == '4');
+  const int lg = (!pow2 && !one_wave && N < 32 && 32 / N > 32 / lgp) ? N : Npad;
+  switch (lg) {
     case 1:
     case 2: launch_fb2_t<2, 1>(c, a, backward); break;
+    case 3: launch_fb2_t<3, 1>(c, a, backward); break;
     case 4: launch_fb2_t<4, 1>(c, a, backward); break;
+    case 5: launch_fb2_t<5, 1>(c, a, backward); break;
+    case 6: launch_fb2_t<6, 1>(c, a, backward); break;
     case 8: launch_fb2_t<8, 1>(c, a, backward); break;
+    case 9: launch_fb2_t<9, 1>(c, a, backward); break;
+    case 10: launch_fb2_t<10, 1>(c, a, backward); break;
     case 16: launch_fb2_t<16, 1>(c, a, backward); break;
     case 32: launch_fb2_t<32, 1>(c, a, backward); break;
     default: launch_fb2_t<32, 2>(c, a, backward); break;   // Npad == 64

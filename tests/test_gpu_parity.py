@@ -319,7 +319,7 @@ def test_register_resident_recursions_four_sequences_per_group(oracle, monkeypat
     want = oracle.estep(q, data)
     sw = oracle.split_stats(q, want)
     gw = oracle.posteriors(q, data)
-    for force in ("4", None):
+    for force in ("4", None):                 # "4" also keeps the exact (non power-of-two) lane groups of N = 3, 5, 10
         if force:
             monkeypatch.setenv("DNBC_FB2_SQ", force)
         else:
