@@ -43,22 +43,20 @@ struct GroupRed {
           sm[q] += __shfl_xor_sync(mask, sm[q], o, LG);
           mx[q] = fmaxf(mx[q], __shfl_xor_sync(mask, mx[q], o, LG));
         }
-      return;
-    }
+    } else {
 #pragma unroll
-    for (int o = P / 2; o > 0; o >>= 1) {
-      const int src = POW2 ? base + (lj ^ o) : base + (lj + o < LG ? lj + o : lj);
-      const bool take = POW2 || (lj < o && lj + o < LG);
+      for (int o = P / 2; o > 0; o >>= 1) {
+        const int src = base + (lj + o < LG ? lj + o : lj);
+        const bool take = lj < o && lj + o < LG;
 #pragma unroll
-      for (int q = 0; q < SQ; ++q) {
-        const float ts = __shfl_sync(mask, sm[q], src), tm = __shfl_sync(mask, mx[q], src);
-        if (take) {
-          sm[q] += ts;
-          mx[q] = fmaxf(mx[q], tm);
+        for (int q = 0; q < SQ; ++q) {
+          const float ts = __shfl_sync(mask, sm[q], src), tm = __shfl_sync(mask, mx[q], src);
+          if (take) {
+            sm[q] += ts;
+            mx[q] = fmaxf(mx[q], tm);
+          }
         }
       }
-    }
-    if (!POW2) {
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         sm[q] = __shfl_sync(mask, sm[q], base);
@@ -73,19 +71,17 @@ struct GroupRed {
       for (int o = LG / 2; o > 0; o >>= 1)
 #pragma unroll
         for (int q = 0; q < SQ; ++q) mx[q] = fmaxf(mx[q], __shfl_xor_sync(mask, mx[q], o, LG));
-      return;
-    }
+    } else {
 #pragma unroll
-    for (int o = P / 2; o > 0; o >>= 1) {
-      const int src = POW2 ? base + (lj ^ o) : base + (lj + o < LG ? lj + o : lj);
-      const bool take = POW2 || (lj < o && lj + o < LG);
+      for (int o = P / 2; o > 0; o >>= 1) {
+        const int src = base + (lj + o < LG ? lj + o : lj);
+        const bool take = lj < o && lj + o < LG;
 #pragma unroll
-      for (int q = 0; q < SQ; ++q) {
-        const float tm = __shfl_sync(mask, mx[q], src);
-        if (take) mx[q] = fmaxf(mx[q], tm);
+        for (int q = 0; q < SQ; ++q) {
+          const float tm = __shfl_sync(mask, mx[q], src);
+          if (take) mx[q] = fmaxf(mx[q], tm);
+        }
       }
-    }
-    if (!POW2) {
 #pragma unroll
       for (int q = 0; q < SQ; ++q) mx[q] = __shfl_sync(mask, mx[q], base);
     }
