@@ -17,7 +17,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DNBC_B200_LIB") or os.path.join(_HERE, "lib", "libdnbc_b200.so")   # override: A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 
-OK, EINVAL, ECUDA, ENODEVICE, ESTATE, ENOMEM = range(6)
+OK, EINVAL, ECUDA, ENODEVICE, ESTATE, ENOMEM, ECOMM = range(7)
+COMM_ID_BYTES = 128
+OPT_MAX_CHUNK_POINTS, OPT_FB2_INTERLEAVE = 1, 2
 DECODE_REFERENCE, DECODE_BACKTRACE = 0, 1
 PREC_F32, PREC_F64 = 0, 1
 QUIRK_TRANSITIONS, DOUBLE_COUNT_FIRST = 1, 2
@@ -29,8 +31,11 @@ SYMBOLS = (
     "dnbc_get_params", "dnbc_upload", "dnbc_generate", "dnbc_download", "dnbc_download_f32", "dnbc_data_shape",
     "dnbc_emission_logprob", "dnbc_supervised_counts", "dnbc_mle", "dnbc_stats_size",
     "dnbc_em_estep", "dnbc_em_estep_streamed", "dnbc_em_stats_device_ptr", "dnbc_em_get_stats", "dnbc_em_set_stats",
-    "dnbc_em_mstep", "dnbc_em_iterate", "dnbc_em_get_posteriors", "dnbc_decode",
-    "dnbc_synchronize", "dnbc_stream", "dnbc_launch_count", "dnbc_profile_enable",
+    "dnbc_em_mstep", "dnbc_em_set_variance_floor", "dnbc_em_floored_components", "dnbc_em_iterate",
+    "dnbc_em_get_posteriors", "dnbc_comm_unique_id", "dnbc_comm_init_rank", "dnbc_comm_init_all", "dnbc_comm_info",
+    "dnbc_comm_destroy", "dnbc_em_allreduce", "dnbc_em_allreduce_group", "dnbc_em_iterate_sharded",
+    "dnbc_em_iterate_group", "dnbc_decode",
+    "dnbc_set_option", "dnbc_synchronize", "dnbc_stream", "dnbc_launch_count", "dnbc_profile_enable",
     "dnbc_profile_read",
 )
 
@@ -60,6 +65,25 @@ class _Config(C.Structure):
 _lib = None
 
 
+def _preload_nccl():
+    """libdnbc_b200.so links libnccl.so.2.  Inside a Python process that also imports torch, load
+    torch's bundled NCCL first so that both resolve the SONAME to the same library (a second,
+    older copy pulled in ahead of torch could miss symbols torch needs)."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        path = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            try:
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -67,6 +91,7 @@ def lib():
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(dnbc_scala_b200 has no CPU fallback)")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH)
         vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
         L.dnbc_abi_version.restype = i32
@@ -93,8 +118,20 @@ def lib():
         L.dnbc_em_set_stats.argtypes = [vp, vp]
         L.dnbc_em_mstep.argtypes = [vp, i64]
         L.dnbc_em_iterate.argtypes = [vp, i32, vp]
+        L.dnbc_em_set_variance_floor.argtypes = [vp, dbl]
+        L.dnbc_em_floored_components.argtypes = [vp, C.POINTER(i64)]
+        L.dnbc_comm_unique_id.argtypes = [vp]
+        L.dnbc_comm_init_rank.argtypes = [vp, i32, i32, vp]
+        L.dnbc_comm_init_all.argtypes = [vp, i32]
+        L.dnbc_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.dnbc_comm_destroy.argtypes = [vp]
+        L.dnbc_em_allreduce.argtypes = [vp]
+        L.dnbc_em_allreduce_group.argtypes = [vp, i32]
+        L.dnbc_em_iterate_sharded.argtypes = [vp, i32, i64, vp]
+        L.dnbc_em_iterate_group.argtypes = [vp, i32, i32, vp]
         L.dnbc_em_get_posteriors.argtypes = [vp, vp]
         L.dnbc_decode.argtypes = [vp, i32, i32, vp, vp, vp]
+        L.dnbc_set_option.argtypes = [vp, i32, i64]
         L.dnbc_synchronize.argtypes = [vp]
         L.dnbc_stream.argtypes = [vp, C.POINTER(vp)]
         L.dnbc_launch_count.argtypes = [vp]
@@ -278,6 +315,36 @@ class Context:
         self._check(lib().dnbc_em_iterate(self._h, n_iters, _p(ll)))
         return ll
 
+    def em_set_variance_floor(self, rel_floor: float):
+        self._check(lib().dnbc_em_set_variance_floor(self._h, float(rel_floor)))
+
+    def em_floored_components(self) -> int:
+        n = C.c_int64(0)
+        self._check(lib().dnbc_em_floored_components(self._h, C.byref(n)))
+        return int(n.value)
+
+    # -- multi-GPU (the library owns the NCCL communicator) ---------------------------
+    def comm_init_rank(self, n_ranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == COMM_ID_BYTES
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._check(lib().dnbc_comm_init_rank(self._h, int(n_ranks), int(rank), C.cast(buf, C.c_void_p)))
+
+    def comm_info(self):
+        n, r = C.c_int(0), C.c_int(0)
+        self._check(lib().dnbc_comm_info(self._h, C.byref(n), C.byref(r)))
+        return int(n.value), int(r.value)
+
+    def comm_destroy(self):
+        self._check(lib().dnbc_comm_destroy(self._h))
+
+    def em_allreduce(self):
+        self._check(lib().dnbc_em_allreduce(self._h))
+
+    def em_iterate_sharded(self, n_iters: int, total_sequences: int) -> np.ndarray:
+        ll = np.zeros(n_iters)
+        self._check(lib().dnbc_em_iterate_sharded(self._h, n_iters, int(total_sequences), _p(ll)))
+        return ll
+
     def em_posteriors(self) -> np.ndarray:
         g = np.zeros((self.P, self.N), np.float32)
         self._check(lib().dnbc_em_get_posteriors(self._h, _p(g)))
@@ -296,6 +363,9 @@ class Context:
         Pinned buffers make the result copies asynchronous DMA transfers."""
         self._check(lib().dnbc_decode(self._h, mode, precision, C.c_void_p(path_ptr or None),
                                       C.c_void_p(score_ptr or None), C.c_void_p(tie_ptr or None)))
+
+    def set_option(self, option: int, value: int):
+        self._check(lib().dnbc_set_option(self._h, int(option), int(value)))
 
     def synchronize(self):
         self._check(lib().dnbc_synchronize(self._h))
@@ -316,3 +386,41 @@ class Context:
         n = np.zeros(len(FAMILIES), np.int64)
         self._check(lib().dnbc_profile_read(self._h, _p(ms), _p(n), int(reset)))
         return dict(zip(FAMILIES, ms.tolist())), dict(zip(FAMILIES, n.tolist()))
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id; rank 0 creates it and ships it to the other ranks."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib().dnbc_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != OK:
+        raise DnbcError(rc, (lib().dnbc_last_error(None) or b"").decode())
+    return buf.raw
+
+
+def _handles(ctxs):
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    return arr
+
+
+def comm_init_all(ctxs):
+    """One process driving several GPUs: join the contexts (one per device) in one communicator."""
+    arr = _handles(ctxs)
+    rc = lib().dnbc_comm_init_all(C.cast(arr, C.c_void_p), len(ctxs))
+    if rc != OK:
+        raise DnbcError(rc, (lib().dnbc_last_error(ctxs[0]._h) or b"").decode())
+
+
+def em_allreduce_group(ctxs):
+    arr = _handles(ctxs)
+    rc = lib().dnbc_em_allreduce_group(C.cast(arr, C.c_void_p), len(ctxs))
+    if rc != OK:
+        raise DnbcError(rc, (lib().dnbc_last_error(ctxs[0]._h) or b"").decode())
+
+
+def em_iterate_group(ctxs, n_iters: int) -> np.ndarray:
+    arr = _handles(ctxs)
+    ll = np.zeros(n_iters)
+    rc = lib().dnbc_em_iterate_group(C.cast(arr, C.c_void_p), len(ctxs), int(n_iters), _p(ll))
+    if rc != OK:
+        raise DnbcError(rc, (lib().dnbc_last_error(ctxs[0]._h) or b"").decode())
+    return ll

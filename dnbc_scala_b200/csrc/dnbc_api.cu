@@ -140,6 +140,9 @@ extern "C" int dnbc_create(const dnbc_config *cfg, dnbc_ctx **out) {
   CREATE_TRY(dev_alloc(&c->d_stats, (size_t)c->stats_size));
   CREATE_TRY(dev_alloc(&c->d_cnt, (size_t)N + (size_t)N * N + (size_t)D * N * Vmax));
   CREATE_TRY(dev_alloc(&c->d_first_seq, N));
+  CREATE_TRY(dev_alloc(&c->d_pooled, C));
+  CREATE_TRY(dev_alloc(&c->d_floored, 1));
+  CREATE_TRY(cudaMemset(c->d_floored, 0, sizeof(unsigned long long)));
   c->h_pinned_bytes = std::max<size_t>(1 << 20, (size_t)c->stats_size * sizeof(double));
   CREATE_TRY(cudaMallocHost((void **)&c->h_pinned, c->h_pinned_bytes));
   if (D) CREATE_TRY(cudaMemcpy(c->d_V, c->V.data(), D * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -155,12 +158,13 @@ extern "C" int dnbc_destroy(dnbc_ctx *c) {
   if (!c) return DNBC_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  dnbc_comm_destroy(c);
   void *ptrs[] = {c->d_pi,    c->d_A,     c->d_B,    c->d_w,      c->d_mu,     c->d_var,   c->d_active, c->d_V,
                   c->d_K,     c->t_pi,    c->t_A,    c->t_At,     c->t_logpi,  c->t_logA,  c->t_cat,    c->t_gs,
                   c->t_gm,    c->t_gc,    c->t64_logpi, c->t64_logA, c->t64_logB, c->t64_u, c->t64_rs,  c->d_off,
                   c->d_disc,  c->d_cont,  c->d_cont64, c->d_labels, c->E,      c->AL,      c->GA,       c->U,
                   c->cs,      c->d_stats, c->E64,    c->d_bp,     c->d_path,   c->d_score, c->d_tie,    c->d_cnt,
-                  c->d_first_seq, c->d_assign, c->d_edge, c->d_edge_i, c->tc_tab, c->tc_x, c->tc_mrow, c->vt_logA};
+                  c->d_first_seq, c->d_assign, c->d_edge, c->d_edge_i, c->tc_tab, c->tc_x, c->tc_mrow, c->vt_logA, c->d_pooled, c->d_floored};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -470,10 +474,7 @@ static int64_t chunk_budget_points(const dnbc_ctx *c, size_t bytes_per_point) {
   size_t budget = std::min<size_t>((free_b + held) / 3, (size_t)48 << 30);
   int64_t pts = (int64_t)(budget / std::max<size_t>(bytes_per_point, 1));
   pts = std::min<int64_t>(pts, (int64_t)1 << 30);   // kernels index chunk-relative points with 32 bits
-  if (const char *cap = getenv("DNBC_MAX_CHUNK_POINTS")) {   // test hook: force the multi-chunk paths on small inputs
-    const long long v = atoll(cap);
-    if (v > 0) pts = std::min<int64_t>(pts, v);
-  }
+  if (c->opt_max_chunk_points > 0) pts = std::min<int64_t>(pts, c->opt_max_chunk_points);   // DNBC_OPT_MAX_CHUNK_POINTS
   pts = std::max<int64_t>(pts, c->Tmax);
   return std::min<int64_t>(pts, std::max<int64_t>(c->P, 1));
 }
@@ -701,6 +702,48 @@ extern "C" int dnbc_em_mstep(dnbc_ctx *c, int64_t total_sequences) {
   return DNBC_OK;
 }
 
+extern "C" int dnbc_set_option(dnbc_ctx *c, int option, int64_t value) {
+  if (!c) return DNBC_EINVAL;
+  switch (option) {
+    case DNBC_OPT_MAX_CHUNK_POINTS:
+      if (value < 0) return dnbc_fail(c, DNBC_EINVAL, "set_option: chunk size must be >= 0");
+      c->opt_max_chunk_points = value;
+      // the scratch arrays shrink with the next E-step / decode
+      CU_TRY(c, cudaSetDevice(c->device));
+      CU_TRY(c, cudaStreamSynchronize(c->stream));
+      {
+        void *old[] = {c->E, c->AL, c->GA, c->U, c->cs};
+        for (void *p : old)
+          if (p) cudaFree(p);
+        c->E = c->AL = c->GA = c->U = c->cs = nullptr;
+        c->scratch_points = 0;
+      }
+      return DNBC_OK;
+    case DNBC_OPT_FB2_INTERLEAVE:
+      c->opt_fb2_interleave = value != 0;
+      return DNBC_OK;
+    default:
+      return dnbc_fail(c, DNBC_EINVAL, "set_option: unknown option %d", option);
+  }
+}
+
+extern "C" int dnbc_em_set_variance_floor(dnbc_ctx *c, double rel_floor) {
+  if (!c) return DNBC_EINVAL;
+  if (!(rel_floor >= 0.0)) return dnbc_fail(c, DNBC_EINVAL, "variance floor must be >= 0");
+  c->var_floor_rel = rel_floor;
+  return DNBC_OK;
+}
+
+extern "C" int dnbc_em_floored_components(dnbc_ctx *c, int64_t *count) {
+  if (!c || !count) return DNBC_EINVAL;
+  CU_TRY(c, cudaSetDevice(c->device));
+  unsigned long long v = 0;
+  CU_TRY(c, cudaMemcpyAsync(&v, c->d_floored, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  *count = (int64_t)v;
+  return DNBC_OK;
+}
+
 extern "C" int dnbc_em_iterate(dnbc_ctx *c, int n_iters, double *loglik_out) {
   if (!c) return DNBC_EINVAL;
   if (c->S == 0) return dnbc_fail(c, DNBC_ESTATE, "em_iterate: no observations resident");
@@ -764,14 +807,7 @@ extern "C" int dnbc_decode(dnbc_ctx *c, int mode, int precision, uint16_t *path_
     if (rc) return rc;
   }
   CU_TRY(c, ensure(&c->d_path, &c->path_cap, c->P));
-  {
-    int64_t cap = c->d_tie ? c->path_cap : 0;
-    if (!c->d_tie || cap < c->P) {
-      if (c->d_tie) cudaFree(c->d_tie);
-      c->d_tie = nullptr;
-      CU_TRY(c, dev_alloc(&c->d_tie, (size_t)c->path_cap));
-    }
-  }
+  CU_TRY(c, ensure(&c->d_tie, &c->tie_cap, c->P));
   CU_TRY(c, ensure(&c->d_score, &c->score_cap, c->S));
   CU_TRY(c, cudaMemsetAsync(c->d_tie, 0, (size_t)c->P, c->stream));
   const size_t per_point = (size_t)N * ((f64 ? sizeof(double) : 4 * sizeof(float)) + (mode == DNBC_DECODE_BACKTRACE ? 2 : 0)) + 8;

@@ -84,6 +84,11 @@ struct dnbc_ctx {
   int64_t scratch_points = 0;
   double *d_stats = nullptr;
   int64_t stats_size = 0;
+  // M-step variance floor (relative to the pooled variance of the observed variable) and the
+  // number of components it raised since the context was created
+  double var_floor_rel = 1e-10;
+  double *d_pooled = nullptr;             // [C]
+  unsigned long long *d_floored = nullptr;
   double *h_pinned = nullptr;   // small pinned bounce buffer
   size_t h_pinned_bytes = 0;
 
@@ -101,7 +106,7 @@ struct dnbc_ctx {
   uint16_t *d_path = nullptr;
   double *d_score = nullptr;
   uint8_t *d_tie = nullptr;
-  int64_t path_cap = 0, score_cap = 0;
+  int64_t path_cap = 0, score_cap = 0, tie_cap = 0;
 
   // supervised learner scratch
   unsigned long long *d_cnt = nullptr;   // [N | N*N | D*N*Vmax]
@@ -110,6 +115,15 @@ struct dnbc_ctx {
   int64_t assign_cap = 0;
   double *d_edge = nullptr;              // per-edge fp64 workspace (layout in k_supervised.cu)
   int32_t *d_edge_i = nullptr;           // per-edge int workspace
+
+  // dnbc_set_option
+  int64_t opt_max_chunk_points = 0;   // 0 = sized from the free memory
+  bool opt_fb2_interleave = false;    // keep the four-sequences-per-lane-group recursions on small inputs
+
+  // library-owned NCCL communicator (dnbc_comm.cu); void* keeps nccl.h out of the kernel files
+  void *comm = nullptr;
+  int comm_ranks = 1, comm_rank = 0;
+  int64_t collectives = 0;
 
   // profiling
   // (event pairs are only recorded, never waited on, while the stream runs; they are
@@ -125,7 +139,10 @@ struct dnbc_ctx {
   DeviceTables tables() const {
     return DeviceTables{t_pi, t_A, t_At, t_logpi, t_logA, t_cat, t_gs, t_gm, t_gc, d_K, d_active};
   }
-  DataView data() const { return DataView{P, d_off, d_disc, d_cont, d_cont64, d_labels}; }
+  // the fp64 planes are only valid for the upload that filled them (a later f32 upload / generate leaves them stale)
+  DataView data() const {
+    return DataView{P, d_off, d_disc, d_cont, have_cont64 ? d_cont64 : nullptr, have_labels ? d_labels : nullptr};
+  }
 };
 
 // statistics buffer offsets (doubles)

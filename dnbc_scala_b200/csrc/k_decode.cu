@@ -432,8 +432,7 @@ void launch_backtrace(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const uin
 }
 
 static bool viterbi2(dnbc_ctx *c, int mode, const DecArgs<float> &a) {
-  static const bool off = getenv("DNBC_NO_VITERBI2") != nullptr;
-  if (off || mode != DNBC_DECODE_BACKTRACE) return false;
+  if (mode != DNBC_DECODE_BACKTRACE) return false;
   switch (c->dm.Npad) {
     case 4: launch_viterbi2_t<4, 1>(c, a); return true;
     case 8: launch_viterbi2_t<8, 1>(c, a); return true;

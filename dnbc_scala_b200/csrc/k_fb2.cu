@@ -506,16 +506,14 @@ template <int LG, int R>
 static void launch_fb2_t(dnbc_ctx *c, const Fb2Args &a, bool backward) {
   constexpr int PG = 32 / LG;
   const int64_t one_wave = (int64_t)c->sm_count * (LG * R > 32 ? 2 : 4) * FB_WARPS * PG;
-  const char *force = getenv("DNBC_FB2_SQ");                // test hook: "4" keeps the interleaved variant on small inputs
-  if (R == 1 && a.s1 - a.s0 <= one_wave && !(force && force[0] == '4')) launch_fb2_sq<LG, R, 1>(c, a, backward);
+  if (R == 1 && a.s1 - a.s0 <= one_wave && !c->opt_fb2_interleave) launch_fb2_sq<LG, R, 1>(c, a, backward);
   else launch_fb2_sq<LG, R, 4>(c, a, backward);
 }
 
 bool fb2_supported(const dnbc_ctx *c) { return c->dm.Npad <= 64; }
 // up to 32 states the backward sweep accumulates the transition statistics itself (launch_xi is then a no-op)
 bool fb2_fuses_xi(const dnbc_ctx *c) {
-  static const bool off = getenv("DNBC_NO_XI_FUSE") != nullptr;
-  return !off && !fb3_supported(c) && fb2_supported(c) && c->dm.Npad <= 32;
+  return !fb3_supported(c) && fb2_supported(c) && c->dm.Npad <= 32;
 }
 
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) {
@@ -523,14 +521,12 @@ void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) 
   Fb2Args a{c->dm, c->tables(), c->d_off, s0, s1, p0, c->E, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi, sl.xi};
   // lanes per group: the padded state count, or the exact one where that puts more sequences into a warp
   // (the rule of lane_group() in k_mixture.cu: N = 3, 5, 6, 9, 10)
-  static const bool pow2 = getenv("DNBC_FB2_POW2") != nullptr;          // A/B switch
   const int N = c->dm.N, Npad = c->dm.Npad;
   // (a chunk that fits one wave of power-of-two groups is latency-bound: the exact groups' extra shuffle round
   // would only lengthen its chain)
   const int lgp = Npad < 32 ? Npad : 32;
-  const char *force = getenv("DNBC_FB2_SQ");                // test hook "4": the large-input kernels on small inputs
-  const bool one_wave = s1 - s0 <= (int64_t)c->sm_count * 4 * FB_WARPS * (32 / lgp) && !(force && force[0] == '4');
-  const int lg = (!pow2 && !one_wave && N < 32 && 32 / N > 32 / lgp) ? N : Npad;
+  const bool one_wave = s1 - s0 <= (int64_t)c->sm_count * 4 * FB_WARPS * (32 / lgp) && !c->opt_fb2_interleave;
+  const int lg = (!one_wave && N < 32 && 32 / N > 32 / lgp) ? N : Npad;
   switch (lg) {
     case 1:
     case 2: launch_fb2_t<2, 1>(c, a, backward); break;

@@ -371,8 +371,7 @@ __global__ void __launch_bounds__(FB3_WARPS * 32, DNBC_FB3_BWD_OCC) k_backward3(
 }  // namespace
 
 bool fb3_supported(const dnbc_ctx *c) {
-  static const bool off = getenv("DNBC_NO_TC") != nullptr || getenv("DNBC_NO_FB3") != nullptr;
-  return !off && c->dm.Npad == NP && c->dm.N % 2 == 0;
+  return c->dm.Npad == NP && c->dm.N % 2 == 0;
 }
 
 void launch_fb3(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) {

@@ -711,8 +711,7 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   // lane group = the state count itself when it is below 32 (N = 10: three points x 10 states fill 30 lanes;
   // the power-of-two group of 16 would fill 20).  Lanes past the last whole group repeat the first points of
   // the next group and store the same values.
-  static const bool pow2lg = getenv("DNBC_EMIT_POW2") != nullptr;
-  const int LG = lane_group(d, pow2lg);
+  const int LG = lane_group(d, false);
   EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, LG, vec};
   const size_t smem = emit_smem(d, KP);
   const int gy = (d.N + 31) / 32;                          // slices of 32 states that hold a real state
@@ -739,13 +738,12 @@ void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
   FamTimer ft(c, FAM_STATS_GMM);
   const Dims &d = c->dm;
   StatsLayout sl = stats_layout(d);
-  static const bool stats_pow2lg = getenv("DNBC_STATS_POW2") != nullptr;   // (A/B switch: power-of-two lane groups)
   int units = d.C > d.D ? d.C : d.D;
   if (units < 1) units = 1;
   const int NW = units > DNBC_STATS_NW ? DNBC_STATS_NW : units;
   const int gz = (units + NW - 1) / NW, gy = (d.N + 31) / 32;
   StatArgs a{d, c->tables(), c->data(), p0, (int)np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
-             c->d_stats + sl.gamma, lane_group(d, stats_pow2lg), NW, 4096};
+             c->d_stats + sl.gamma, lane_group(d, false), NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
   // 16 warps per SM (128 registers each): CTAs of NW warps, e.g. 3 x 5 warps when 5 variables
 #ifdef DNBC_STATS_PER_SM

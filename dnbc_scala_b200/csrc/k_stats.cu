@@ -209,6 +209,9 @@ void launch_stats_cat(dnbc_ctx *c, int64_t p0, int64_t np) {
 //   B_d[j][v] = cat / sum_v cat                        (same)
 //   w = s0 / sum_k s0, mu += s1/s0, var = s2/s0 - (s1/s0)^2   (EM1D.java:104-132)
 // A row / edge whose denominator is zero keeps its previous parameters.
+// The reference's EM1D has no variance floor (a collapsed component gives var = 0 and NaN
+// responsibilities, EM1D.java:92-101); Baum-Welch over many iterations needs one: a new variance
+// below var_floor_rel x (pooled variance of that observed variable) is raised to it and counted.
 // ---------------------------------------------------------------------------------
 struct MstepArgs {
   Dims dm;
@@ -217,7 +220,43 @@ struct MstepArgs {
   StatsLayout sl;
   double S;
   double *pi, *A, *B, *w, *mu, *var;
+  double floor_rel;
+  double *pooled;                 // [C] pooled variance per continuous variable (k_pooled_variance)
+  unsigned long long *floored;    // [1]
 };
+
+// pooled variance of variable c over every state and component, from the moments centred on the
+// old means: x = z + mu_old  =>  sum x = s1 + mu s0,  sum x^2 = s2 + 2 mu s1 + mu^2 s0
+__global__ void k_pooled_variance(MstepArgs a) {
+  const int N = a.dm.N, Kmax = a.dm.Kmax, c = blockIdx.x;
+  __shared__ double sh[3][128];
+  double n = 0.0, sx = 0.0, sxx = 0.0;
+  for (int q = threadIdx.x; q < N * Kmax; q += blockDim.x) {
+    if (q % Kmax >= a.K[c]) continue;
+    const int64_t e = (int64_t)c * N * Kmax + q;
+    const double *x = a.st + a.sl.gmm + 3 * e;
+    const double mu = a.mu[e];
+    n += x[0];
+    sx += x[1] + mu * x[0];
+    sxx += x[2] + 2.0 * mu * x[1] + mu * mu * x[0];
+  }
+  sh[0][threadIdx.x] = n; sh[1][threadIdx.x] = sx; sh[2][threadIdx.x] = sxx;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+      for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double tn = sh[0][0];
+    double v = 0.0;
+    if (tn > 0.0) {
+      const double m = sh[1][0] / tn;
+      v = sh[2][0] / tn - m * m;
+    }
+    a.pooled[c] = v > 0.0 ? v : 0.0;
+  }
+}
 
 __global__ void k_mstep(MstepArgs a) {
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax;
@@ -240,6 +279,7 @@ __global__ void k_mstep(MstepArgs a) {
       const int q = r - N - N * D, c = q / N, j = q % N;
       const int64_t base = ((int64_t)c * N + j) * Kmax;
       const double *x = a.st + a.sl.gmm + 3 * base;
+      const double vfloor = a.floor_rel * a.pooled[c];
       double tot = 0.0;
       for (int k = 0; k < a.K[c]; ++k) tot += x[3 * k];
       if (tot > 0.0)
@@ -248,8 +288,13 @@ __global__ void k_mstep(MstepArgs a) {
           a.w[base + k] = s0 / tot;
           if (s0 > 0.0) {
             const double sh = s1 / s0;
+            double v = s2 / s0 - sh * sh;
+            if (!(v >= vfloor)) {      // also catches a NaN from cancellation on an empty component
+              v = vfloor;
+              atomicAdd(a.floored, 1ull);
+            }
             a.mu[base + k] += sh;
-            a.var[base + k] = s2 / s0 - sh * sh;
+            a.var[base + k] = v;
           }
         }
     } else {
@@ -262,8 +307,12 @@ void launch_mstep(dnbc_ctx *c, int64_t total_sequences) {
   {
     FamTimer ft(c, FAM_MSTEP);
     MstepArgs a{c->dm, c->d_V, c->d_K, c->d_stats, stats_layout(c->dm), (double)total_sequences,
-                c->d_pi, c->d_A, c->d_B, c->d_w, c->d_mu, c->d_var};
+                c->d_pi, c->d_A, c->d_B, c->d_w, c->d_mu, c->d_var, c->var_floor_rel, c->d_pooled, c->d_floored};
     const int rows = c->dm.N * (1 + c->dm.D + c->dm.C) + 1;
+    if (c->dm.C > 0) {
+      k_pooled_variance<<<c->dm.C, 128, 0, c->stream>>>(a);
+      c->launches++;
+    }
     k_mstep<<<(rows + 127) / 128, 128, 0, c->stream>>>(a);
   }
   c->tables64_valid = false;

@@ -609,8 +609,7 @@ __global__ void k_tc_tables(const double *__restrict__ A, int N, int NP, unsigne
 }  // namespace
 
 bool fb_tc_supported(const dnbc_ctx *c) {
-  static const bool off = getenv("DNBC_NO_TC") != nullptr;
-  return !off && (c->dm.Npad == 256 || c->dm.Npad == 512);
+  return c->dm.Npad == 256 || c->dm.Npad == 512;
 }
 
 void launch_tc_tables(dnbc_ctx *c) {

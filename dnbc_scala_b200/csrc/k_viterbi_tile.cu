@@ -290,8 +290,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
 }  // namespace
 
 bool viterbi_tile_supported(const dnbc_ctx *c) {
-  static const bool off = getenv("DNBC_NO_VITERBI2") != nullptr;
-  return !off && c->dm.Npad >= VT_JC && c->dm.Npad % VT_JC == 0 && c->dm.Npad <= 1024;
+  return c->dm.Npad >= VT_JC && c->dm.Npad % VT_JC == 0 && c->dm.Npad <= 1024;
 }
 
 int launch_viterbi_tile(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path, double *score,

@@ -250,8 +250,7 @@ void launch_t(dnbc_ctx *c, XiArgs a, int ctas_per_sm) {
 }  // namespace
 
 bool xi_tc_supported(const dnbc_ctx *c) {
-  static const bool off = getenv("DNBC_NO_TC") != nullptr;
-  return !off && c->dm.N >= 64;
+  return c->dm.N >= 64;
 }
 
 void launch_xi_tc(dnbc_ctx *c, int64_t np) {

@@ -183,13 +183,43 @@ def parse_lines(lines: Iterable[str]) -> DataSet:
     return DataSet(types, vocab, learn, test)
 
 
-def load(path: str) -> DataSet:
+def reorder_states_scala(ds: DataSet) -> DataSet:
+    """Renumber hidden states in the iteration order of the reference's `transitions` map
+    (first appearance as a transition source, then Scala's immutable-Map order), so that the
+    device's "lowest dense index wins" tie-breaking means what `maxBy` over that map means
+    (DynamicNaiveBayesianClassifier.scala:75, :85, :89; scala_compat.py).  In place."""
+    from .scala_compat import scala_map_order
+    L = ds.learn
+    src_mask = np.ones(L.P, bool)
+    src_mask[L.offsets[1:] - 1] = False            # the last step of a sequence is not a transition source
+    src = L.labels[src_mask]
+    _, first = np.unique(src, return_index=True)
+    from_order = [ds.vocab.states[i] for i in src[np.sort(first)]]
+    order = scala_map_order(from_order)
+    order += [s for s in ds.vocab.states if s not in set(order)]
+    remap = np.array([order.index(s) for s in ds.vocab.states], np.int32)
+    for part in (ds.learn, ds.test):
+        if part.labels is not None and part.P:
+            lab = part.labels.copy()
+            part.labels = np.where(lab >= 0, remap[np.maximum(lab, 0)], -1).astype(np.int32)
+    ds.vocab.states = order
+    ds.vocab.state_id = {s: i for i, s in enumerate(order)}
+    return ds
+
+
+def load(path: str, reference_state_order: bool = False) -> DataSet:
+    """Parse a `.data` file.  Hidden states are numbered in first-seen order; with
+    reference_state_order=True they are renumbered in the reference's Map iteration order
+    (reorder_states_scala), which is what decides EXACT decode ties on the device -- pass it
+    whenever paths are to be compared with the reference's at ties (Measure does)."""
     if path.endswith(".gz"):
         import gzip
         with gzip.open(path, "rt") as fh:
-            return parse_lines(fh)
-    with open(path, "r") as fh:
-        return parse_lines(fh)
+            ds = parse_lines(fh)
+    else:
+        with open(path, "r") as fh:
+            ds = parse_lines(fh)
+    return reorder_states_scala(ds) if reference_state_order else ds
 
 
 def write(path: str, types: Sequence[str], vocab: Vocabulary, learn: DenseSequences,

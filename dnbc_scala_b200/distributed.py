@@ -7,7 +7,8 @@ contiguous block of sequences, runs the E-step on it, and a single
 all-reduce(sum, float64) of the packed sufficient-statistics buffer
 [LL | pi | xi | gamma | categorical | GMM moments] (include/dnbc_b200.h) merges the shards;
 the M-step then runs identically on every rank, so no broadcast is needed.  Decode needs no
-collective at all.
+collective at all.  The all-reduce itself is behind the C ABI (include/dnbc_b200.h,
+`dnbc_comm_*` / `dnbc_em_allreduce`, csrc/dnbc_comm.cu).
 
 The buffer is 312 KB at the scale-out configuration (N=64, D=16, C=16, K=8): latency-bound
 on NVLink 5 / NVSwitch, launched on the same stream as the E-step kernels.
@@ -26,39 +27,35 @@ def shard_range(n_sequences: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(n_sequences, lo + per)
 
 
-class _DevicePtrArray:
-    """Zero-copy view of the device statistics buffer for torch (CUDA array interface v2)."""
-
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-
 class StatsAllReduce:
-    """all-reduce(sum) of a context's statistics buffer over torch.distributed.
+    """all-reduce(sum) of a context's statistics buffer across the ranks of a torch.distributed job.
 
-    backend nccl: in place on the device buffer, enqueued on the context's own stream.
+    backend nccl: the collective is the LIBRARY's (`dnbc_em_allreduce`: ncclAllReduce(sum, f64) on
+    the context's own stream with a communicator the library owns); torch.distributed only carries
+    the 128-byte unique id from rank 0 to the other ranks once -- the role a Spark broadcast
+    variable plays in the JVM shim.  Nothing on the data plane goes through torch.
     backend gloo: staged through host memory (CPU tests of the multi-rank logic).
     """
 
     def __init__(self, ctx, group=None):
         import torch
         import torch.distributed as dist
+        from . import _native as nat
         self.ctx, self.group, self.dist, self.torch = ctx, group, dist, torch
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.backend = dist.get_backend(group) if dist.is_initialized() else None
-        self._tensor = None
-        self._stream = None
         if self.world > 1 and self.backend == "nccl":
-            n = ctx.stats_size()
-            self._tensor = torch.as_tensor(_DevicePtrArray(ctx.em_stats_device_ptr(), n), device=torch.device("cuda", ctx.device))
-            self._stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", ctx.device))
+            rank = dist.get_rank(group)
+            box = [nat.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group,
+                                       device=torch.device("cuda", ctx.device))
+            ctx.comm_init_rank(self.world, rank, box[0])
 
     def __call__(self):
         if self.world == 1:
             return
         if self.backend == "nccl":
-            with self.torch.cuda.stream(self._stream):
-                self.dist.all_reduce(self._tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.ctx.em_allreduce()
         else:
             st = self.torch.from_numpy(np.ascontiguousarray(self.ctx.em_get_stats()))
             self.dist.all_reduce(st, op=self.dist.ReduceOp.SUM, group=self.group)

@@ -49,7 +49,8 @@ enum {
   DNBC_ECUDA = 2,       /* CUDA runtime error                                           */
   DNBC_ENODEVICE = 3,   /* no usable GPU: the product has no CPU path                    */
   DNBC_ESTATE = 4,      /* call order (e.g. decode before upload)                       */
-  DNBC_ENOMEM = 5
+  DNBC_ENOMEM = 5,
+  DNBC_ECOMM = 6        /* NCCL error                                                   */
 };
 
 /* decode modes.  REFERENCE reproduces viterbiCompute
@@ -136,17 +137,55 @@ int dnbc_em_estep(dnbc_ctx *ctx, int clamp_labels);
  * stay resident afterwards; host buffers should be pinned.  labels may be NULL. */
 int dnbc_em_estep_streamed(dnbc_ctx *ctx, int64_t n_seq, const int64_t *offsets, const uint8_t *disc,
                            const float *cont_f32, const int32_t *labels, int clamp_labels);
-/* device address of the statistics buffer (for an NCCL all-reduce by the host) */
+/* device address of the statistics buffer (test hook; the all-reduce is dnbc_em_allreduce) */
 int dnbc_em_stats_device_ptr(dnbc_ctx *ctx, void **ptr);
 int dnbc_em_get_stats(dnbc_ctx *ctx, double *stats);
 int dnbc_em_set_stats(dnbc_ctx *ctx, const double *stats);
 /* M-step from the statistics buffer; total_sequences = S summed over all shards */
 int dnbc_em_mstep(dnbc_ctx *ctx, int64_t total_sequences);
+/* Variance floor of the M-step.  The reference's per-edge EM has none (a collapsed component
+ * gives var = 0 and NaN responsibilities, Tools/ExpectationMaximization1D.java:92-124); here a new
+ * variance below rel_floor x (pooled variance of that observed variable) is raised to that value.
+ * Default 1e-10; 0 disables.  dnbc_em_floored_components: how many components were raised since
+ * dnbc_create. */
+int dnbc_em_set_variance_floor(dnbc_ctx *ctx, double rel_floor);
+int dnbc_em_floored_components(dnbc_ctx *ctx, int64_t *count);
 /* n_iters x (E-step, M-step) on one GPU; loglik_out[i] = log-likelihood of the
  * parameters entering iteration i */
 int dnbc_em_iterate(dnbc_ctx *ctx, int n_iters, double *loglik_out);
 /* posterior state marginals gamma [P][N] f32 of the last E-step (test hook) */
 int dnbc_em_get_posteriors(dnbc_ctx *ctx, float *gamma);
+
+/* ---- multi-GPU: sequences shard over contexts, one statistics all-reduce per iteration ------
+ * Replaces the reference's three Spark scatter/gather rounds through the driver
+ * (DynamicNaiveBayesianClassifier.scala:231-232, 241-243, 250-252).  Every context holds its own
+ * block of sequences; after the local E-step one ncclAllReduce(sum, ncclDouble) of the packed
+ * statistics buffer, enqueued on the context's stream, leaves the global statistics on every GPU
+ * and the M-step runs identically everywhere (no broadcast).  Decode needs no collective.
+ *
+ * Two ways to form the communicator, both owned by the library:
+ *   (a) one process (or thread) per GPU: rank 0 calls dnbc_comm_unique_id and ships the 128 bytes
+ *       to the other ranks by any means (the JVM shim: a Spark broadcast variable); every rank
+ *       then calls dnbc_comm_init_rank on its context;
+ *   (b) one process driving several GPUs (the reference's single driver thread): create one
+ *       context per device and call dnbc_comm_init_all on the array; collectives for all of
+ *       them are then issued together with dnbc_em_allreduce_group / dnbc_em_iterate_group.
+ * Without a communicator (a single GPU) dnbc_em_allreduce is a no-op. */
+#define DNBC_COMM_ID_BYTES 128
+int dnbc_comm_unique_id(uint8_t id[DNBC_COMM_ID_BYTES]);
+int dnbc_comm_init_rank(dnbc_ctx *ctx, int n_ranks, int rank, const uint8_t id[DNBC_COMM_ID_BYTES]);
+int dnbc_comm_init_all(dnbc_ctx **ctxs, int n_ctx);
+int dnbc_comm_info(const dnbc_ctx *ctx, int *n_ranks, int *rank);
+int dnbc_comm_destroy(dnbc_ctx *ctx);
+/* in-place all-reduce(sum, f64) of the statistics buffer on the context's stream (asynchronous) */
+int dnbc_em_allreduce(dnbc_ctx *ctx);
+/* the same for contexts formed with dnbc_comm_init_all (one ncclGroup over all of them) */
+int dnbc_em_allreduce_group(dnbc_ctx **ctxs, int n_ctx);
+/* n_iters x (local E-step, all-reduce, M-step with total_sequences = S over all shards): (a) is
+ * called by every rank on its own context; (b) drives all contexts from the calling thread.
+ * loglik_out[i] = GLOBAL log-likelihood of the parameters entering iteration i. */
+int dnbc_em_iterate_sharded(dnbc_ctx *ctx, int n_iters, int64_t total_sequences, double *loglik_out);
+int dnbc_em_iterate_group(dnbc_ctx **ctxs, int n_ctx, int n_iters, double *loglik_out);
 
 /* ---- decode (K5): replaces inferMostLikelyHiddenStates / score ----------------- */
 /* path_out u16 [P]; score_out f64 [S] (REFERENCE: sum_j delta_{T-1}(j), 0 for T == 1;
@@ -155,6 +194,17 @@ int dnbc_em_get_posteriors(dnbc_ctx *ctx, float *gamma);
  * equality in F64; relative margin in F32).  Any output may be NULL. */
 int dnbc_decode(dnbc_ctx *ctx, int mode, int precision, uint16_t *path_out, double *score_out,
                 uint8_t *tie_out);
+
+/* ---- tuning / test options (none is needed in normal use; the library reads no environment) --- */
+enum {
+  /* cap on the points per E-step / decode chunk; 0 = sized from the free HBM.  Small values force
+   * the multi-chunk pipelines on small inputs (tests). */
+  DNBC_OPT_MAX_CHUNK_POINTS = 1,
+  /* 1 = keep the register-resident recursions (N <= 64) on their large-input variant -- four
+   * sequences per lane group, exact lane groups -- for inputs that fit one wave (tests). */
+  DNBC_OPT_FB2_INTERLEAVE = 2
+};
+int dnbc_set_option(dnbc_ctx *ctx, int option, int64_t value);
 
 /* ---- streams / timing hooks ---------------------------------------------------- */
 int dnbc_synchronize(dnbc_ctx *ctx);

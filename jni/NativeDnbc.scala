@@ -31,6 +31,10 @@ class NativeDnbc private (private var handle: Long, val nStates: Int, val alphab
   @native private def nEmGetStats(h: Long, stats: Array[Double]): Int
   @native private def nEmSetStats(h: Long, stats: Array[Double]): Int
   @native private def nEmMstep(h: Long, totalSequences: Long): Int
+  @native private def nCommInitRank(h: Long, nRanks: Int, rank: Int, id: Array[Byte]): Int
+  @native private def nCommDestroy(h: Long): Int
+  @native private def nEmAllreduce(h: Long): Int
+  @native private def nEmIterateSharded(h: Long, iters: Int, totalSequences: Long, loglik: Array[Double]): Int
 
   private val vmax = if (alphabet.isEmpty) 1 else alphabet.max
   private val kmax = if (mixture.isEmpty) 1 else mixture.max
@@ -74,7 +78,19 @@ class NativeDnbc private (private var handle: Long, val nStates: Int, val alphab
     ll
   }
 
-  // multi-GPU: one NativeDnbc per device; per iteration estep() on each, sum the statistics, mstep() on each
+  // multi-GPU, one executor process per GPU: the driver creates the id once (NativeDnbc.commUniqueId()),
+  // ships it in a Spark broadcast variable, every executor joins and iterates on its own shard;
+  // the statistics all-reduce is the library's (ncclAllReduce over NVLink, include/dnbc_b200.h)
+  def commInitRank(nRanks: Int, rank: Int, id: Array[Byte]): Unit = check(nCommInitRank(handle, nRanks, rank, id))
+  def commDestroy(): Unit = check(nCommDestroy(handle))
+  def allreduce(): Unit = check(nEmAllreduce(handle))
+  def emIterateSharded(iters: Int, totalSequences: Long): Array[Double] = {
+    val ll = new Array[Double](iters)
+    check(nEmIterateSharded(handle, iters, totalSequences, ll))
+    ll
+  }
+
+  // finer-grained pieces of one iteration
   def statsSize: Int = nStatsSize(handle).toInt
   def estep(clampLabels: Boolean = false): Unit = check(nEmEstep(handle, clampLabels))
   def getStats(): Array[Double] = { val s = new Array[Double](statsSize); check(nEmGetStats(handle, s)); s }
@@ -92,6 +108,28 @@ object NativeDnbc {
   val QuirkTransitions = 1; val DoubleCountFirst = 2        // supervised-learner switches (SURVEY F3, F4)
 
   @native private def nCreate(nStates: Int, alphabet: Array[Int], mixture: Array[Int], device: Int): Long
+  @native private def nCommUniqueId(id: Array[Byte]): Int
+  @native private def nCommInitAll(handles: Array[Long]): Int
+  @native private def nEmIterateGroup(handles: Array[Long], iters: Int, loglik: Array[Double]): Int
+
+  /** 128-byte NCCL unique id for commInitRank (created on the driver, broadcast to the executors) */
+  def commUniqueId(): Array[Byte] = {
+    val id = new Array[Byte](128)
+    if (nCommUniqueId(id) != 0) throw new Exception("dnbc_comm_unique_id failed")
+    id
+  }
+
+  /** one JVM driving several GPUs (the reference's single driver thread): join one instance per device ... */
+  def commInitAll(models: Seq[NativeDnbc]): Unit =
+    if (nCommInitAll(models.map(_.handle).toArray) != 0) throw new Exception(models.head.nLastError(models.head.handle))
+
+  /** ... and run Baum-Welch over all of them: local E-steps, one all-reduce, replicated M-steps per iteration */
+  def emIterateGroup(models: Seq[NativeDnbc], iters: Int): Array[Double] = {
+    val ll = new Array[Double](iters)
+    if (nEmIterateGroup(models.map(_.handle).toArray, iters, ll) != 0)
+      throw new Exception(models.head.nLastError(models.head.handle))
+    ll
+  }
 
   /** throws Exception("Number of suggested normal distributions ... at least one") for a hint < 1, like :276 */
   def create(nStates: Int, alphabet: Seq[Int], mixture: Seq[Int], device: Int = 0): NativeDnbc = {

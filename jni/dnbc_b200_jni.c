@@ -3,10 +3,15 @@
  *
  * Binds the natives of jni/NativeDnbc.scala (the class a maintainer adds next to
  * core/src/main/scala/DynamicNaiveBayesianClassifier.scala) to the C ABI of
- * include/dnbc_b200.h.  Pure marshalling: every function pins the JVM arrays, calls the
- * dnbc_* entry point of the same name and returns its status; the Scala side turns a non-zero
- * status into `new Exception(nLastError(handle))`, the reference's error convention
- * (DynamicNaiveBayesianClassifier.scala:46, 148, 274, 276).
+ * include/dnbc_b200.h.  Pure marshalling: every function copies the JVM arrays into native
+ * staging buffers, calls the dnbc_* entry point of the same name and returns its status; the
+ * Scala side turns a non-zero status into `new Exception(nLastError(handle))`, the reference's
+ * error convention (DynamicNaiveBayesianClassifier.scala:46, 148, 274, 276).
+ *
+ * JNI critical regions (GetPrimitiveArrayCritical) must not block: they stall the collector for
+ * every thread of the Spark executor JVM.  So a region here only ever brackets one memcpy between
+ * the JVM array and a malloc'ed staging buffer (copy_in / copy_out); cudaMalloc, kernels, stream
+ * synchronisation and NCCL all run outside of it.
  *
  * Build (needs a JDK, which this repository's image does not have):
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude \
@@ -17,15 +22,44 @@
 #include <jni.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "dnbc_b200.h"
 
 #define CTX(h) ((dnbc_ctx *)(intptr_t)(h))
 
-/* pinned views of (possibly null) JVM primitive arrays */
-static void *pin(JNIEnv *env, jarray a) { return a ? (*env)->GetPrimitiveArrayCritical(env, a, NULL) : NULL; }
-static void unpin(JNIEnv *env, jarray a, void *p, jint mode) {
-  if (a) (*env)->ReleasePrimitiveArrayCritical(env, a, p, mode);
+/* native copy of a (possibly null) JVM primitive array; NULL for a null or empty array */
+static void *copy_in(JNIEnv *env, jarray a, size_t elem) {
+  if (!a) return NULL;
+  const size_t bytes = (size_t)(*env)->GetArrayLength(env, a) * elem;
+  void *buf = malloc(bytes ? bytes : 1);
+  if (!buf) return NULL;
+  void *p = (*env)->GetPrimitiveArrayCritical(env, a, NULL);
+  if (p) {
+    memcpy(buf, p, bytes);
+    (*env)->ReleasePrimitiveArrayCritical(env, a, p, JNI_ABORT);
+  }
+  return buf;
+}
+
+/* zeroed native buffer the size of a (possibly null) JVM array, for outputs */
+static void *alloc_out(JNIEnv *env, jarray a, size_t elem) {
+  if (!a) return NULL;
+  const size_t bytes = (size_t)(*env)->GetArrayLength(env, a) * elem;
+  return calloc(bytes ? bytes : 1, 1);
+}
+
+/* copies a native output buffer back into its JVM array and frees it */
+static void copy_out(JNIEnv *env, jarray a, void *buf, size_t elem) {
+  if (!a || !buf) return;
+  const size_t bytes = (size_t)(*env)->GetArrayLength(env, a) * elem;
+  void *p = (*env)->GetPrimitiveArrayCritical(env, a, NULL);
+  if (p) {
+    memcpy(p, buf, bytes);
+    (*env)->ReleasePrimitiveArrayCritical(env, a, p, 0);
+  }
+  free(buf);
 }
 
 JNIEXPORT jlong JNICALL Java_NativeDnbc_nCreate(JNIEnv *env, jobject self, jint n_states, jintArray alphabet,
@@ -35,14 +69,14 @@ JNIEXPORT jlong JNICALL Java_NativeDnbc_nCreate(JNIEnv *env, jobject self, jint 
   cfg.n_states = n_states;
   cfg.n_disc = alphabet ? (*env)->GetArrayLength(env, alphabet) : 0;
   cfg.n_cont = mixture ? (*env)->GetArrayLength(env, mixture) : 0;
-  jint *al = (jint *)pin(env, alphabet), *mx = (jint *)pin(env, mixture);
-  cfg.alphabet = (const int32_t *)al;
-  cfg.mixture = (const int32_t *)mx;
+  int32_t *al = copy_in(env, alphabet, sizeof(jint)), *mx = copy_in(env, mixture, sizeof(jint));
+  cfg.alphabet = al;
+  cfg.mixture = mx;
   cfg.device = device;
   dnbc_ctx *ctx = NULL;
   const int rc = dnbc_create(&cfg, &ctx);
-  unpin(env, mixture, mx, JNI_ABORT);
-  unpin(env, alphabet, al, JNI_ABORT);
+  free(mx);
+  free(al);
   if (rc != DNBC_OK) {
     /* e.g. "Number of suggested normal distributions in a continuous variable must be at least one" (:276) */
     (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/Exception"), dnbc_last_error(NULL));
@@ -65,11 +99,11 @@ JNIEXPORT jint JNICALL Java_NativeDnbc_nSetParams(JNIEnv *env, jobject self, jlo
                                                   jdoubleArray b, jdoubleArray w, jdoubleArray mu, jdoubleArray var,
                                                   jbyteArray active) {
   (void)self;
-  double *ppi = pin(env, pi), *pa = pin(env, a), *pb = pin(env, b), *pw = pin(env, w), *pmu = pin(env, mu), *pv = pin(env, var);
-  uint8_t *pact = pin(env, active);
+  double *ppi = copy_in(env, pi, 8), *pa = copy_in(env, a, 8), *pb = copy_in(env, b, 8), *pw = copy_in(env, w, 8),
+         *pmu = copy_in(env, mu, 8), *pv = copy_in(env, var, 8);
+  uint8_t *pact = copy_in(env, active, 1);
   const int rc = dnbc_set_params(CTX(h), ppi, pa, pb, pw, pmu, pv, pact);
-  unpin(env, active, pact, JNI_ABORT); unpin(env, var, pv, JNI_ABORT); unpin(env, mu, pmu, JNI_ABORT);
-  unpin(env, w, pw, JNI_ABORT); unpin(env, b, pb, JNI_ABORT); unpin(env, a, pa, JNI_ABORT); unpin(env, pi, ppi, JNI_ABORT);
+  free(pact); free(pv); free(pmu); free(pw); free(pb); free(pa); free(ppi);
   return rc;
 }
 
@@ -77,12 +111,12 @@ JNIEXPORT jint JNICALL Java_NativeDnbc_nGetParams(JNIEnv *env, jobject self, jlo
                                                   jdoubleArray b, jdoubleArray w, jdoubleArray mu, jdoubleArray var,
                                                   jbyteArray active) {
   (void)self;
-  double *ppi = pin(env, pi), *pa = pin(env, a), *pb = pin(env, b), *pw = pin(env, w), *pmu = pin(env, mu), *pv = pin(env, var);
-  uint8_t *pact = pin(env, active);
+  double *ppi = alloc_out(env, pi, 8), *pa = alloc_out(env, a, 8), *pb = alloc_out(env, b, 8), *pw = alloc_out(env, w, 8),
+         *pmu = alloc_out(env, mu, 8), *pv = alloc_out(env, var, 8);
+  uint8_t *pact = alloc_out(env, active, 1);
   const int rc = dnbc_get_params(CTX(h), ppi, pa, pb, pw, pmu, pv, pact);
-  /* mode 0: copy the results back into the JVM arrays */
-  unpin(env, active, pact, 0); unpin(env, var, pv, 0); unpin(env, mu, pmu, 0);
-  unpin(env, w, pw, 0); unpin(env, b, pb, 0); unpin(env, a, pa, 0); unpin(env, pi, ppi, 0);
+  copy_out(env, active, pact, 1); copy_out(env, var, pv, 8); copy_out(env, mu, pmu, 8);
+  copy_out(env, w, pw, 8); copy_out(env, b, pb, 8); copy_out(env, a, pa, 8); copy_out(env, pi, ppi, 8);
   return rc;
 }
 
@@ -90,13 +124,12 @@ JNIEXPORT jint JNICALL Java_NativeDnbc_nGetParams(JNIEnv *env, jobject self, jlo
 JNIEXPORT jint JNICALL Java_NativeDnbc_nUpload(JNIEnv *env, jobject self, jlong h, jlong n_seq, jlongArray offsets,
                                                jbyteArray disc, jdoubleArray cont, jintArray labels) {
   (void)self;
-  int64_t *po = pin(env, offsets);
-  uint8_t *pd = pin(env, disc);
-  double *pc = pin(env, cont);
-  int32_t *pl = pin(env, labels);
-  const int rc = dnbc_upload(CTX(h), n_seq, po, pd, pc, NULL, pl);   /* the library copies: arrays are released on return */
-  unpin(env, labels, pl, JNI_ABORT); unpin(env, cont, pc, JNI_ABORT); unpin(env, disc, pd, JNI_ABORT);
-  unpin(env, offsets, po, JNI_ABORT);
+  int64_t *po = copy_in(env, offsets, 8);
+  uint8_t *pd = copy_in(env, disc, 1);
+  double *pc = copy_in(env, cont, 8);
+  int32_t *pl = copy_in(env, labels, 4);
+  const int rc = dnbc_upload(CTX(h), n_seq, po, pd, pc, NULL, pl);   /* the library copies again, to the device */
+  free(pl); free(pc); free(pd); free(po);
   return rc;
 }
 
@@ -104,9 +137,9 @@ JNIEXPORT jint JNICALL Java_NativeDnbc_nUpload(JNIEnv *env, jobject self, jlong 
 JNIEXPORT jint JNICALL Java_NativeDnbc_nMle(JNIEnv *env, jobject self, jlong h, jint flags, jdoubleArray init_centroids,
                                             jint max_iters, jdouble rel_tol) {
   (void)self;
-  double *pc = pin(env, init_centroids);
+  double *pc = copy_in(env, init_centroids, 8);
   const int rc = dnbc_mle(CTX(h), flags, pc, max_iters, rel_tol, NULL, NULL);
-  unpin(env, init_centroids, pc, JNI_ABORT);
+  free(pc);
   return rc;
 }
 
@@ -114,24 +147,88 @@ JNIEXPORT jint JNICALL Java_NativeDnbc_nMle(JNIEnv *env, jobject self, jlong h, 
 JNIEXPORT jint JNICALL Java_NativeDnbc_nDecode(JNIEnv *env, jobject self, jlong h, jint mode, jint precision,
                                                jshortArray path, jdoubleArray score, jbyteArray tie) {
   (void)self;
-  uint16_t *pp = pin(env, path);
-  double *ps = pin(env, score);
-  uint8_t *pt = pin(env, tie);
+  uint16_t *pp = alloc_out(env, path, 2);
+  double *ps = alloc_out(env, score, 8);
+  uint8_t *pt = alloc_out(env, tie, 1);
   const int rc = dnbc_decode(CTX(h), mode, precision, pp, ps, pt);
-  unpin(env, tie, pt, 0); unpin(env, score, ps, 0); unpin(env, path, pp, 0);
+  copy_out(env, tie, pt, 1); copy_out(env, score, ps, 8); copy_out(env, path, pp, 2);
   return rc;
 }
 
 /* Baum-Welch (new, additive): n_iters x (E-step, M-step) on this context's GPU */
 JNIEXPORT jint JNICALL Java_NativeDnbc_nEmIterate(JNIEnv *env, jobject self, jlong h, jint n_iters, jdoubleArray loglik) {
   (void)self;
-  double *pl = pin(env, loglik);
+  double *pl = alloc_out(env, loglik, 8);
   const int rc = dnbc_em_iterate(CTX(h), n_iters, pl);
-  unpin(env, loglik, pl, 0);
+  copy_out(env, loglik, pl, 8);
   return rc;
 }
 
-/* multi-GPU learning from the JVM: one context per GPU, statistics summed by the caller */
+/* ---- multi-GPU learning: the library owns the NCCL communicator and the all-reduce ----------------
+ * replaces the three Spark parallelize/map/collect rounds of learnFinalize (:231-232, 241-243, 250-252) */
+JNIEXPORT jint JNICALL Java_NativeDnbc_nCommUniqueId(JNIEnv *env, jobject self, jbyteArray id) {
+  (void)self;
+  if (!id || (*env)->GetArrayLength(env, id) != DNBC_COMM_ID_BYTES) return DNBC_EINVAL;
+  uint8_t *p = alloc_out(env, id, 1);
+  const int rc = dnbc_comm_unique_id(p);
+  copy_out(env, id, p, 1);
+  return rc;
+}
+JNIEXPORT jint JNICALL Java_NativeDnbc_nCommInitRank(JNIEnv *env, jobject self, jlong h, jint n_ranks, jint rank,
+                                                     jbyteArray id) {
+  (void)self;
+  if (!id || (*env)->GetArrayLength(env, id) != DNBC_COMM_ID_BYTES) return DNBC_EINVAL;
+  uint8_t *p = copy_in(env, id, 1);
+  const int rc = dnbc_comm_init_rank(CTX(h), n_ranks, rank, p);
+  free(p);
+  return rc;
+}
+/* one JVM driving several GPUs: handles = the dnbc_ctx of every device, in rank order */
+static dnbc_ctx **ctx_array(JNIEnv *env, jlongArray handles, int *n) {
+  *n = handles ? (*env)->GetArrayLength(env, handles) : 0;
+  jlong *hs = copy_in(env, handles, sizeof(jlong));
+  dnbc_ctx **ctxs = calloc(*n > 0 ? (size_t)*n : 1, sizeof(dnbc_ctx *));
+  for (int i = 0; ctxs && hs && i < *n; ++i) ctxs[i] = CTX(hs[i]);
+  free(hs);
+  return ctxs;
+}
+JNIEXPORT jint JNICALL Java_NativeDnbc_nCommInitAll(JNIEnv *env, jobject self, jlongArray handles) {
+  (void)self;
+  int n = 0;
+  dnbc_ctx **ctxs = ctx_array(env, handles, &n);
+  const int rc = ctxs ? dnbc_comm_init_all(ctxs, n) : DNBC_ENOMEM;
+  free(ctxs);
+  return rc;
+}
+JNIEXPORT jint JNICALL Java_NativeDnbc_nCommDestroy(JNIEnv *env, jobject self, jlong h) {
+  (void)env; (void)self;
+  return dnbc_comm_destroy(CTX(h));
+}
+JNIEXPORT jint JNICALL Java_NativeDnbc_nEmAllreduce(JNIEnv *env, jobject self, jlong h) {
+  (void)env; (void)self;
+  return dnbc_em_allreduce(CTX(h));
+}
+JNIEXPORT jint JNICALL Java_NativeDnbc_nEmIterateSharded(JNIEnv *env, jobject self, jlong h, jint n_iters,
+                                                         jlong total_sequences, jdoubleArray loglik) {
+  (void)self;
+  double *pl = alloc_out(env, loglik, 8);
+  const int rc = dnbc_em_iterate_sharded(CTX(h), n_iters, total_sequences, pl);
+  copy_out(env, loglik, pl, 8);
+  return rc;
+}
+JNIEXPORT jint JNICALL Java_NativeDnbc_nEmIterateGroup(JNIEnv *env, jobject self, jlongArray handles, jint n_iters,
+                                                       jdoubleArray loglik) {
+  (void)self;
+  int n = 0;
+  dnbc_ctx **ctxs = ctx_array(env, handles, &n);
+  double *pl = alloc_out(env, loglik, 8);
+  const int rc = ctxs ? dnbc_em_iterate_group(ctxs, n, n_iters, pl) : DNBC_ENOMEM;
+  copy_out(env, loglik, pl, 8);
+  free(ctxs);
+  return rc;
+}
+
+/* finer-grained pieces (an application that interleaves its own work between the phases) */
 JNIEXPORT jlong JNICALL Java_NativeDnbc_nStatsSize(JNIEnv *env, jobject self, jlong h) {
   (void)env; (void)self;
   return (jlong)dnbc_stats_size(CTX(h));
@@ -142,16 +239,16 @@ JNIEXPORT jint JNICALL Java_NativeDnbc_nEmEstep(JNIEnv *env, jobject self, jlong
 }
 JNIEXPORT jint JNICALL Java_NativeDnbc_nEmGetStats(JNIEnv *env, jobject self, jlong h, jdoubleArray stats) {
   (void)self;
-  double *p = pin(env, stats);
+  double *p = alloc_out(env, stats, 8);
   const int rc = dnbc_em_get_stats(CTX(h), p);
-  unpin(env, stats, p, 0);
+  copy_out(env, stats, p, 8);
   return rc;
 }
 JNIEXPORT jint JNICALL Java_NativeDnbc_nEmSetStats(JNIEnv *env, jobject self, jlong h, jdoubleArray stats) {
   (void)self;
-  double *p = pin(env, stats);
+  double *p = copy_in(env, stats, 8);
   const int rc = dnbc_em_set_stats(CTX(h), p);
-  unpin(env, stats, p, JNI_ABORT);
+  free(p);
   return rc;
 }
 JNIEXPORT jint JNICALL Java_NativeDnbc_nEmMstep(JNIEnv *env, jobject self, jlong h, jlong total_sequences) {

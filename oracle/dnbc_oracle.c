@@ -32,6 +32,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py's CPU arms set this explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static int64_t total_points(const orc_data *d) { return d->off[d->S]; }
 
 /* ------------------------------------------------------------------------- */
@@ -582,10 +591,14 @@ void orc_posteriors(const orc_model *m, const orc_data *data, double *gamma_out)
  * DiscreteEdge.learnFinalize Edge.scala:53-59 and the EM1D M-step EM1D.java:104-132
  * (variance around the new mean: s2/s0 - (s1/s0)^2 for moments centred on the old
  * mean).  A row/edge whose denominator is zero keeps its previous parameters. */
-void orc_mstep(orc_model *m, const double *st, int64_t S) {
+/* M-step with the product's variance floor: a new variance below floor_rel x (pooled variance of
+ * that observed variable, from the same statistics) is raised to it; *floored counts them.  The
+ * reference's EM1D has no floor (EM1D.java:120-124); floor_rel = 0 restates it exactly. */
+void orc_mstep_floor(orc_model *m, const double *st, int64_t S, double floor_rel, int64_t *floored) {
   const int N = m->N, D = m->D, C = m->C, Vmax = m->Vmax, Kmax = m->Kmax;
   const double *S_pi = st + 1, *S_xi = S_pi + N, *S_g = S_xi + (int64_t)N * N;
   const double *S_cat = S_g + N, *S_gmm = S_cat + (int64_t)D * N * Vmax;
+  int64_t nfl = 0;
   for (int j = 0; j < N; ++j) m->pi[j] = S_pi[j] / (double)S;
   for (int i = 0; i < N; ++i) {
     double sum = 0.0;
@@ -599,7 +612,18 @@ void orc_mstep(orc_model *m, const double *st, int64_t S) {
       for (int v = 0; v < m->V[d]; ++v) sum += row[v];
       if (sum > 0.0) for (int v = 0; v < m->V[d]; ++v) m->B[((int64_t)d * N + j) * Vmax + v] = row[v] / sum;
     }
-  for (int c = 0; c < C; ++c)
+  for (int c = 0; c < C; ++c) {
+    /* pooled variance of variable c: x = z + mu_old */
+    double n = 0.0, sx = 0.0, sxx = 0.0, pooled = 0.0;
+    for (int j = 0; j < N; ++j)
+      for (int k = 0; k < m->K[c]; ++k) {
+        const int64_t e = ((int64_t)c * N + j) * Kmax + k;
+        const double mu = m->mu[e], s0 = S_gmm[3 * e], s1 = S_gmm[3 * e + 1], s2 = S_gmm[3 * e + 2];
+        n += s0; sx += s1 + mu * s0; sxx += s2 + 2.0 * mu * s1 + mu * mu * s0;
+      }
+    if (n > 0.0) { const double mean = sx / n; pooled = sxx / n - mean * mean; }
+    if (!(pooled > 0.0)) pooled = 0.0;
+    const double vfloor = floor_rel * pooled;
     for (int j = 0; j < N; ++j) {
       const int64_t base = ((int64_t)c * N + j) * Kmax;
       double tot = 0.0;
@@ -610,9 +634,15 @@ void orc_mstep(orc_model *m, const double *st, int64_t S) {
         m->w[base + k] = s0 / tot;
         if (s0 > 0.0) {
           double sh = s1 / s0;
+          double v = s2 / s0 - sh * sh;
+          if (!(v >= vfloor)) { v = vfloor; ++nfl; }
           m->mu[base + k] += sh;
-          m->var[base + k] = s2 / s0 - sh * sh;
+          m->var[base + k] = v;
         }
       }
     }
+  }
+  if (floored) *floored = nfl;
 }
+
+void orc_mstep(orc_model *m, const double *st, int64_t S) { orc_mstep_floor(m, st, S, 1e-10, 0); }

@@ -105,7 +105,8 @@ void orc_decode(const orc_model *m, const orc_data *data, int mode, int32_t *pat
  */
 int64_t orc_stats_size(const orc_model *m);
 void orc_estep(const orc_model *m, const orc_data *data, int clamp_labels, double *stats);
-void orc_mstep(orc_model *m, const double *stats, int64_t S);
+void orc_mstep(orc_model *m, const double *stats, int64_t S);   /* floor_rel = 1e-10, the product's default */
+void orc_mstep_floor(orc_model *m, const double *stats, int64_t S, double floor_rel, int64_t *floored);
 /* gamma_out [P][N] optional posterior dump for tests */
 void orc_posteriors(const orc_model *m, const orc_data *data, double *gamma_out);
 
@@ -113,6 +114,7 @@ void orc_posteriors(const orc_model *m, const orc_data *data, double *gamma_out)
 double orc_accuracy(const orc_data *data, const int32_t *path);
 
 int orc_num_threads(void);
+void orc_set_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,8 @@ def lib():
         L.orc_stats_size.restype = C.c_int64
         L.orc_accuracy.restype = C.c_double
         L.orc_mstep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_mstep_floor.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_int]
         L.orc_normalize_counts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
         _lib = L
@@ -231,9 +233,17 @@ def estep(model: Model, data: Data, clamp_labels: bool = False) -> np.ndarray:
     return st
 
 
-def mstep(model: Model, stats: np.ndarray, S: int) -> None:
+def mstep(model: Model, stats: np.ndarray, S: int, floor_rel: Optional[float] = None) -> int:
+    """M-step in place.  floor_rel: the variance floor relative to the variable's pooled variance
+    (None = the product's default 1e-10, 0 = none, as the reference's EM1D); returns how many
+    component variances were raised to the floor."""
     stats = np.ascontiguousarray(stats, np.float64)
-    lib().orc_mstep(model.ref, _p(stats), S)
+    if floor_rel is None:
+        lib().orc_mstep(model.ref, _p(stats), S)
+        return 0
+    n = C.c_int64(0)
+    lib().orc_mstep_floor(model.ref, _p(stats), S, float(floor_rel), C.byref(n))
+    return int(n.value)
 
 
 def em_iterate(model: Model, data: Data, n_iters: int) -> np.ndarray:
@@ -267,6 +277,10 @@ def split_stats(model: Model, st: np.ndarray):
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(int(n))
 
 
 # ---------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 """Randomised parity sweep: random shapes / mixtures / ragged lengths, CUDA path vs the fp64 oracle.
-usage: python tests/fuzz_parity.py [cases] [seed]   (needs a B200; prints the first failure and exits 1)"""
+usage: python tests/fuzz_parity.py [cases] [seed] [mle|large]   (needs a B200; prints the first failure and exits 1)
+  mle   = supervised learner cases;  large = N in {256, 300, 512} with sequences of up to 400 steps"""
 import os
 import sys
 
@@ -21,17 +22,22 @@ def flagged_or_equal(path, opath, tie, otie, off, backtrace):
     return all(flagged[off[s]:(off[s + 1] if backtrace else n + 1)].any() for n, s in zip(diff, seq_of))
 
 
-def one(case, rng):
-    N = int(rng.choice([1, 2, 3, 5, 6, 7, 9, 10, 12, 16, 17, 31, 32, 33, 48, 63, 64, 65, 96, 128, 130, 200, 256, 300]))
+def one(case, rng, large=False):
+    N = int(rng.choice([256, 300, 512] if large else
+                       [1, 2, 3, 5, 6, 7, 9, 10, 12, 16, 17, 31, 32, 33, 48, 63, 64, 65, 96, 128, 130, 200, 256, 300]))
     D = int(rng.integers(0, 4))
     C = int(rng.integers(0, 4)) if D else int(rng.integers(1, 4))
     V = [int(rng.integers(2, 12)) for _ in range(D)]
     K = [int(rng.integers(1, 9)) for _ in range(C)]
     tps = int(rng.integers(1, min(N, 12) + 1))
     m = random_model(oracle, N, V, K, int(rng.integers(1 << 30)), transitions_per_state=tps, unit_var=bool(rng.integers(2)))
-    nseq = int(rng.integers(1, 50))
+    nseq = int(rng.integers(4, 14)) if large else int(rng.integers(1, 50))
     tmax = int(rng.choice([1, 3, 20, 90, 400] if os.environ.get("FUZZ_LONG") else [1, 3, 20, 90]))
-    lengths = [int(x) for x in rng.integers(0, tmax + 1, nseq)]
+    if large:      # long dependency chains at tensor-core state counts: most sequences run the full length
+        tmax = int(rng.choice([200, 400]))
+        lengths = [tmax if rng.random() < 0.6 else int(rng.integers(0, tmax + 1)) for _ in range(nseq)]
+    else:
+        lengths = [int(x) for x in rng.integers(0, tmax + 1, nseq)]
     if sum(lengths) == 0:
         lengths[0] = 2
     data = sample(oracle, m, lengths, int(rng.integers(1 << 30)))
@@ -43,11 +49,8 @@ def one(case, rng):
     opath, oscore, otie = oracle.decode(q, data, oracle.DECODE_BACKTRACE)
     rpath, rscore, rtie = oracle.decode(q, data, oracle.DECODE_REFERENCE)
     # (every other case keeps the register-resident recursions on their four-sequences-per-group variant)
-    if case % 2:
-        os.environ["DNBC_FB2_SQ"] = "4"
-    else:
-        os.environ.pop("DNBC_FB2_SQ", None)
     with ctx_for(nat, q) as ctx:
+        ctx.set_option(nat.OPT_FB2_INTERLEAVE, case % 2)
         upload(ctx, data, labels=False)
         ctx.em_estep()
         got = ctx.em_get_stats()
@@ -154,13 +157,13 @@ def main():
         return
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 12345)
+    large = len(sys.argv) > 3 and sys.argv[3] == "large"
     done = skipped = 0
     for case in range(cases):
-        if one(case, rng) is None:
+        if one(case, rng, large) is None:
             skipped += 1
         else:
             done += 1
-    os.environ.pop("DNBC_FB2_SQ", None)
     print(f"fuzz ok: {done} cases compared, {skipped} skipped (zero-probability data)")
 
 

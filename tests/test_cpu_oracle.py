@@ -229,3 +229,61 @@ def test_jni_glue_type_checks_against_the_abi():
     natives_c = set(re.findall(r"Java_NativeDnbc_(n\w+)", open(glue).read()))
     natives_scala = set(re.findall(r"@native private def (n\w+)", open(os.path.join(root, "jni", "NativeDnbc.scala")).read()))
     assert natives_c == natives_scala and len(natives_c) >= 14, (natives_c ^ natives_scala)
+
+
+def test_split_known_answers(oracle):
+    """DataSet.scala:48-49 discards the result of `lines.dropWhile(..).drop(1)`; if Scala's Iterator.dropWhile
+    is lazy the reference would score the LEARNING sequences.  The two readings give different accuracies on
+    robot_no_momentum.data, and only the test split satisfies the reference's own assertion `> 65`
+    (DynamicNaiveBayesianClassifierTest.scala:13) and the published 65 % (README.md:11) -- which is why
+    measure.Measure defaults to split="test" and offers split="learn" for the other reading."""
+    ds = dataset.load(os.path.join(GOLDEN, "robot_no_momentum.data.gz"), reference_state_order=True)
+    learn, test = oracle.Data.of(ds.learn), oracle.Data.of(ds.test)
+    m = oracle.mle(learn, ds.N, ds.V, None, flags=oracle.QUIRK_TRANSITIONS)
+    acc = {}
+    for name, part in (("test", test), ("learn", learn)):
+        path, _, _ = oracle.decode(m, part, oracle.DECODE_REFERENCE)
+        acc[name] = oracle.accuracy(part, path)
+    assert abs(acc["test"] - 65.232) < 2e-3 and acc["test"] > 65
+    assert abs(acc["learn"] - 64.925) < 2e-3 and not acc["learn"] > 65
+
+
+def test_reference_state_order_only_renumbers(oracle):
+    """dataset.load(reference_state_order=True) permutes the dense state ids (Scala Map iteration order,
+    which decides exact ties) and nothing else: same names per point, same supervised counts up to the
+    permutation."""
+    path = os.path.join(GOLDEN, "robot_no_momentum_bivariate.data.gz")
+    a, b = dataset.load(path), dataset.load(path, reference_state_order=True)
+    assert sorted(a.vocab.states) == sorted(b.vocab.states) and a.vocab.states != b.vocab.states
+    names_a = [a.vocab.states[i] for i in a.learn.labels[:5000]]
+    names_b = [b.vocab.states[i] for i in b.learn.labels[:5000]]
+    assert names_a == names_b
+    assert b.vocab.states[:5] == scala_map_order(b.vocab.states)[:5]
+    ca = oracle.mle_counts(a.N, max(a.V), oracle.Data.of(a.learn), 0)
+    cb = oracle.mle_counts(b.N, max(b.V), oracle.Data.of(b.learn), 0)
+    perm = [a.vocab.states.index(s) for s in b.vocab.states]
+    np.testing.assert_array_equal(cb[1], ca[1][np.ix_(perm, perm)])
+
+
+def test_oracle_mstep_variance_floor(oracle):
+    """orc_mstep_floor: floor_rel = 0 restates the reference's unfloored EM1D M-step (EM1D.java:120-124);
+    a positive floor only touches components below floor_rel x pooled variance and counts them."""
+    m = random_model(oracle, 3, [], [2], 5)
+    data = sample(oracle, m, [30] * 5, 6)
+    st = oracle.estep(m, data)
+    a, b, c = m.copy(), m.copy(), m.copy()
+    assert oracle.mstep(a, st, data.S, floor_rel=0.0) == 0
+    assert oracle.mstep(b, st, data.S) == 0                      # default floor 1e-10 never fires on healthy data
+    np.testing.assert_array_equal(a.var, b.var)
+    n = oracle.mstep(c, st, data.S, floor_rel=1e3)               # absurdly high floor: every component is raised
+    assert n == 6 and np.allclose(c.var, c.var.flat[0]) and (c.var > a.var).all()
+    np.testing.assert_array_equal(a.mu, c.mu)
+
+
+def test_library_reads_no_environment():
+    """north_star: no multi-backend dispatch.  The round-1 A/B getenv switches are gone; tuning / test hooks
+    go through dnbc_set_option."""
+    csrc = os.path.join(os.path.dirname(GOLDEN), "..", "dnbc_scala_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh")):
+            assert "getenv" not in open(os.path.join(csrc, f)).read(), f

@@ -306,9 +306,9 @@ def test_every_state_count_dispatch_path_matches_oracle(oracle, N):
 
 
 @pytest.mark.parametrize("N", [2, 3, 5, 10, 12, 17, 32])
-def test_register_resident_recursions_four_sequences_per_group(oracle, monkeypatch, N):
+def test_register_resident_recursions_four_sequences_per_group(oracle, N):
     """k_fb2.cu advances one sequence per lane group on small inputs and four interleaved ones on large
-    inputs (DNBC_FB2_SQ=4 forces the latter here), and up to 32 states its backward sweep accumulates the
+    inputs (dnbc_set_option DNBC_OPT_FB2_INTERLEAVE forces the latter here), and up to 32 states its backward sweep accumulates the
     transition statistics itself: both variants against the fp64 oracle, ragged lengths, every lane-group
     size (2 .. 32 lanes), with the emission / statistics sweeps on exact (non power-of-two) lane groups."""
     m = random_model(oracle, N, [4, 3], [2, 3], 900 + N, transitions_per_state=min(N, 6))
@@ -319,12 +319,9 @@ def test_register_resident_recursions_four_sequences_per_group(oracle, monkeypat
     want = oracle.estep(q, data)
     sw = oracle.split_stats(q, want)
     gw = oracle.posteriors(q, data)
-    for force in ("4", None):                 # "4" also keeps the exact (non power-of-two) lane groups of N = 3, 5, 10
-        if force:
-            monkeypatch.setenv("DNBC_FB2_SQ", force)
-        else:
-            monkeypatch.delenv("DNBC_FB2_SQ", raising=False)
+    for force in (1, 0):                      # 1 also keeps the exact (non power-of-two) lane groups of N = 3, 5, 10
         with ctx_for(nat, q) as ctx:
+            ctx.set_option(nat.OPT_FB2_INTERLEAVE, force)
             upload(ctx, data, labels=False, dtype=np.float32)
             ctx.em_estep()
             sg = oracle.split_stats(q, ctx.em_get_stats())
@@ -415,10 +412,10 @@ def test_empty_sequences_between_real_ones(oracle, N):
     np.testing.assert_allclose(s32, oscore, rtol=1e-5)
 
 
-def test_chunked_pipelines_equal_single_chunk(oracle, monkeypatch):
+def test_chunked_pipelines_equal_single_chunk(oracle):
     """The E-step, the streamed (upload-overlapped) E-step and the decoders walk the resident
     sequences in chunks of whole sequences when the scratch does not hold them all.  With the
-    chunk size forced down to 300 points (DNBC_MAX_CHUNK_POINTS) every pipeline must reproduce
+    chunk size forced down to 300 points (dnbc_set_option DNBC_OPT_MAX_CHUNK_POINTS) every pipeline must reproduce
     its single-chunk result on ragged sequences, for the FP32 and the tensor-core recursions."""
     for N in (10, 64):
         m = random_model(oracle, N, [5, 3], [2, 3], 700 + N, transitions_per_state=min(N, 8))
@@ -426,7 +423,6 @@ def test_chunked_pipelines_equal_single_chunk(oracle, monkeypatch):
         lengths = [int(x) for x in rng.integers(1, 120, 41)] + [1, 299, 300, 2]
         data = sample(oracle, m, lengths, 720 + N)
         q = perturb(oracle, m, 730 + N)
-        monkeypatch.delenv("DNBC_MAX_CHUNK_POINTS", raising=False)
         with ctx_for(nat, q) as ctx:
             upload(ctx, data, labels=False, dtype=np.float32)
             ctx.em_estep()
@@ -434,8 +430,8 @@ def test_chunked_pipelines_equal_single_chunk(oracle, monkeypatch):
             g_want = ctx.em_posteriors()
             p_want, s_want, t_want = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
             r_want, rs_want, _ = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
-        monkeypatch.setenv("DNBC_MAX_CHUNK_POINTS", "300")
         with ctx_for(nat, q) as ctx:
+            ctx.set_option(nat.OPT_MAX_CHUNK_POINTS, 300)
             upload(ctx, data, labels=False, dtype=np.float32)
             ctx.em_estep()
             got = ctx.em_get_stats()
@@ -451,7 +447,6 @@ def test_chunked_pipelines_equal_single_chunk(oracle, monkeypatch):
             np.testing.assert_array_equal(r, r_want)
             np.testing.assert_allclose(rs, rs_want, rtol=1e-12)
             ll = ctx.em_iterate(2)
-        monkeypatch.delenv("DNBC_MAX_CHUNK_POINTS")
         with ctx_for(nat, q) as ctx:
             upload(ctx, data, labels=False, dtype=np.float32)
             np.testing.assert_allclose(ctx.em_iterate(2), ll, rtol=1e-7)
