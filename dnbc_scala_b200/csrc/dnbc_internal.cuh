@@ -182,6 +182,8 @@ bool mixture_emission_fast(const dnbc_ctx *c);
 bool mixture_stats_fast(const dnbc_ctx *c);
 void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out);
 void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np);
+bool stats2_supported(const dnbc_ctx *c);
+int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np);
 bool fb3_supported(const dnbc_ctx *c);
 void launch_fb3(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 bool fb2_supported(const dnbc_ctx *c);

@@ -732,17 +732,31 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   }
 }
 
-// GMM moments + categorical histograms + gamma sums in one sweep over the posteriors
+// GMM moments + categorical histograms + gamma sums in one sweep over the posteriors.
+// State counts that are a multiple of 32 go through k_stats2.cu (whole 32-point blocks); k_stats_pk takes every
+// other shape and the ragged tail.
+static void launch_stats_pk(dnbc_ctx *c, int64_t p0, int64_t np, const float *GA);
 void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np) {
   if (np <= 0) return;
   FamTimer ft(c, FAM_STATS_GMM);
+  int64_t done = 0;
+#ifndef DNBC_NO_STATS2              // (A/B builds only: tools/build_variant.sh)
+  if (stats2_supported(c)) done = launch_stats2(c, p0, np);
+#endif
+  if (done < np) {
+    if (done) c->launches++;
+    launch_stats_pk(c, p0 + done, np - done, c->GA + done * c->dm.N);
+  }
+}
+
+static void launch_stats_pk(dnbc_ctx *c, int64_t p0, int64_t np, const float *GA) {
   const Dims &d = c->dm;
   StatsLayout sl = stats_layout(d);
   int units = d.C > d.D ? d.C : d.D;
   if (units < 1) units = 1;
   const int NW = units > DNBC_STATS_NW ? DNBC_STATS_NW : units;
   const int gz = (units + NW - 1) / NW, gy = (d.N + 31) / 32;
-  StatArgs a{d, c->tables(), c->data(), p0, (int)np, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
+  StatArgs a{d, c->tables(), c->data(), p0, (int)np, GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
              c->d_stats + sl.gamma, lane_group(d, false), NW, 4096};
   const size_t smem = (size_t)NW * (d.Vmax + 1) * 32 * sizeof(float);
   // 16 warps per SM (128 registers each): CTAs of NW warps, e.g. 3 x 5 warps when 5 variables

@@ -1,0 +1,382 @@
+// k_stats2.cu -- K3 statistics sweep, second generation, for state counts that are a multiple of 32
+// (the scale-out shape N = 64 and the large-state shape N = 512).
+//
+// Same mathematics and the same fp32-window / fp64-flush scheme as k_stats_pk (k_mixture.cu): GMM
+// responsibilities and moments (generalising the E- and M-step sums of EM1D.run,
+// core/src/main/java/Tools/ExpectationMaximization1D.java:92-124), categorical histograms
+// (DiscreteEdge.learn, core/src/main/scala/Edge.scala:46-51) and the gamma sums.
+//
+// Why a second kernel: ncu on k_stats_pk<4> (profiles/r01f_ncu_summary.txt) shows 73 warp instructions
+// per (point, variable, 32 states) against 74 MUFU cycles: the sweep is ISSUE-bound, and 18 of the 73
+// are register moves, 64-bit address arithmetic and predicate bookkeeping around the posterior
+// prefetch (8 MOV, 3.7 IADD3, 3 FSETP, 1.4 LEA, 1 IMAD, 1 ISETP).  Here nothing is carried in
+// registers across points except the coefficients, the accumulators and the two pipeline buffers:
+//   * the posteriors of a 32-point x 32-state block arrive in shared memory through cp.async
+//     (8 x 16 B per lane per block, double buffered, one block ahead) and are read back with one
+//     conflict-free LDS per point: no prefetch registers, no rotation moves, no long-scoreboard stalls;
+//   * the observation of a point is warp-uniform: the lane that loaded it stores the record
+//     {x, x, 128 * symbol} once per block and every point costs one broadcast LDS.128 that yields the
+//     packed pair (x, x) and the histogram row offset (no shuffle, no duplicate move);
+//   * blocks are always whole (the launcher gives the ragged tail to k_stats_pk), lanes are always
+//     real states: no predicates in the loop.
+// Per point and warp: 32 packed fp32 + 9 MUFU + ~13 other instructions.
+#include "dnbc_internal.cuh"
+#include "packed_f32.cuh"
+
+namespace {
+
+constexpr int NW_MAX = 8;        // warps per CTA, one observed variable each
+#ifndef S2_PTS
+#define S2_PTS 8                 // points per trip of the block loop (ptxas pays ~30 register moves per trip)
+#endif
+
+struct Stat2Args {
+  Dims dm;
+  DeviceTables tb;
+  DataView dv;
+  int64_t p0;
+  int nblk;                      // whole 32-point blocks of this launch
+  const float *GA;
+  const double *mu_old;
+  double *gmm, *cat, *gsum;
+  int window;                    // points per fp32 accumulation window (multiple of 32)
+  int nw;                        // warps per CTA
+};
+
+__device__ __forceinline__ u64 ex2_2(u64 a) {
+  u64 d;
+  asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tex2.approx.ftz.f32 lo, lo;\n\tex2.approx.ftz.f32 hi, hi;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}" : "=l"(d) : "l"(a));
+  return d;
+}
+__device__ __forceinline__ float hsum(u64 a) {
+  float lo, hi;
+  unpk(a, lo, hi);
+  return lo + hi;
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int KP>
+struct Coef {
+  u64 s2[KP], m2[KP], cc2[KP];   // z = x s + m ; exponent = cc - z^2 (log2 units), two components per register pair
+};
+template <int KP>
+struct Acc {
+  u64 S0[KP], S1[KP], S2[KP];    // sum r, sum r z, sum r z^2 over the current window
+};
+template <int KP>
+struct Pend {
+  u64 z[KP], e[KP];
+};
+
+// stage 1 of a point: standardised coordinate and the 2 KP exponentials
+template <int KP>
+__device__ __forceinline__ void stage1(const Coef<KP> &q, u64 xx, Pend<KP> &n) {
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    n.z[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
+    n.e[kp] = ex2_2(fnma2(n.z[kp], n.z[kp], q.cc2[kp]));
+  }
+}
+// mixture sum of a pending point (the underflow decision is taken on exactly this value, here and in the redo)
+template <int KP>
+__device__ __forceinline__ float mix_sum(const Pend<KP> &p) {
+  u64 sum2 = p.e[0];
+#pragma unroll
+  for (int kp = 1; kp < KP; ++kp) sum2 = add2(sum2, p.e[kp]);
+  return hsum(sum2);
+}
+// stage 2: normalise by the mixture sum, weight by the posterior, accumulate the three moments.
+// No predicates: the sum is clamped to the smallest normal float, so the weight g / sum is finite and a mixture
+// whose every component flushed to zero contributes exactly nothing.  The weight itself is the underflow detector:
+// the caller keeps its running maximum and a value above HBIG (sum < 1e-18 g: the state carries posterior mass
+// at a point ~9 sigma away from all of its components, where fp32 has flushed part of the mixture) sends the
+// block through the exponent-shifted re-evaluation.
+constexpr float HBIG = 1e18f;
+template <int KP>
+__device__ __forceinline__ float stage2(Acc<KP> &a, const Pend<KP> &p, float g) {
+  const float sum = mix_sum<KP>(p);
+  const float inv = g * rcp_approx(fmaxf(sum, 1.17549435e-38f));
+  const u64 inv2 = pk(inv, inv);
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    const u64 rr = mul2(p.e[kp], inv2);
+    a.S0[kp] = add2(a.S0[kp], rr);
+    const u64 rz = mul2(rr, p.z[kp]);
+    a.S1[kp] = add2(a.S1[kp], rz);
+    a.S2[kp] = fma2(rz, p.z[kp], a.S2[kp]);
+  }
+  return inv;
+}
+// exponent-shifted evaluation for a point whose mixture sum underflows fp32 (rare; same as stat_point of k_mixture.cu)
+template <int KP>
+__device__ __forceinline__ void shifted_point(const Coef<KP> &q, Acc<KP> &a, float x, float g) {
+  const u64 xx = pk(x, x);
+  u64 a2[KP], z2[KP];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    z2[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
+    a2[kp] = fnma2(z2[kp], z2[kp], q.cc2[kp]);
+    float lo, hi;
+    unpk(a2[kp], lo, hi);
+    mx = fmaxf(mx, fmaxf(lo, hi));
+  }
+  mx = mx == -INFINITY ? 0.f : mx;
+  const u64 nm = pk(-mx, -mx);
+  u64 sum2 = 0ull;
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    a2[kp] = ex2_2(add2(a2[kp], nm));
+    sum2 = add2(sum2, a2[kp]);
+  }
+  const float sum = hsum(sum2);
+  const float inv = sum > 0.f ? g * rcp_approx(sum) : 0.f;
+  const u64 inv2 = pk(inv, inv);
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    const u64 rr = mul2(a2[kp], inv2);
+    a.S0[kp] = add2(a.S0[kp], rr);
+    const u64 rz = mul2(rr, z2[kp]);
+    a.S1[kp] = add2(a.S1[kp], rz);
+    a.S2[kp] = fma2(rz, z2[kp], a.S2[kp]);
+  }
+}
+
+// shared memory of one warp: posterior tiles (2 stages), observation records (2 stages, 33 entries: the pipeline
+// reads one record past the block), histogram rows
+struct alignas(16) Rec { float x0, x1; int voff; int pad; };
+
+// One 32-point block.  gt = this lane's column of the posterior tile (stride 32 floats per point), rec = the block's
+// observation records, bdb = this lane's histogram column as a byte address (rows are 128 bytes apart and the
+// record carries 128 * symbol).  Four points per loop trip with constant offsets from two bumped pointers; the two
+// pipeline buffers alternate, so nothing is copied between points.  Returns the largest weight g / sum seen.
+template <int KP, bool HAS_C, bool HAS_D>
+__device__ __forceinline__ float block32(const Coef<KP> &q, Acc<KP> &acc, const float *gt, const Rec *rec, char *bdb, float &gsl,
+                                         bool gsum_on) {
+  float hmax = 0.f;
+  Pend<KP> pa, pb;
+  if (HAS_C) {
+    const float4 r0 = *reinterpret_cast<const float4 *>(rec);
+    stage1<KP>(q, pk(r0.x, r0.y), pa);
+  }
+  const float4 *rp = reinterpret_cast<const float4 *>(rec);
+#pragma unroll 1
+  for (int it = 0; it < 32 / S2_PTS; ++it, rp += S2_PTS, gt += 32 * S2_PTS) {
+#pragma unroll
+    for (int h = 0; h < S2_PTS; h += 2) {
+      const float g0 = gt[32 * h], g1 = gt[32 * h + 32];
+      if (HAS_C) {
+        const float2 x1 = *reinterpret_cast<const float2 *>(rp + h + 1);
+        stage1<KP>(q, pk(x1.x, x1.y), pb);
+        hmax = fmaxf(hmax, stage2<KP>(acc, pa, g0));
+        const float2 x2 = *reinterpret_cast<const float2 *>(rp + h + 2);
+        stage1<KP>(q, pk(x2.x, x2.y), pa);
+        hmax = fmaxf(hmax, stage2<KP>(acc, pb, g1));
+      }
+      if (HAS_D) {
+        // categorical histogram: bins[symbol][state] += gamma
+        const int v0 = __float_as_int(rp[h].z), v1 = __float_as_int(rp[h + 1].z);
+        *reinterpret_cast<float *>(bdb + v0) += g0;
+        *reinterpret_cast<float *>(bdb + v1) += g1;
+      }
+      if (gsum_on) gsl += g0 + g1;
+    }
+  }
+  return hmax;
+}
+
+#ifndef S2_MAXREG
+#define S2_MAXREG 128
+#endif
+template <int KP>
+__global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.y * 32 + lane;                     // always a real state (N % 32 == 0)
+  const int u = blockIdx.z * a.nw + w;                      // this warp's variable index
+  const bool has_c = u < C, has_d = u < D;
+  if (!has_c && !has_d) return;
+  const int bin_floats = (Vmax + 1) * 32;
+  const size_t per_warp = (size_t)2 * 32 * 32 * sizeof(float) + 2 * 34 * sizeof(Rec) + (size_t)bin_floats * sizeof(float);
+  unsigned char *base_w = smem_raw + (size_t)w * per_warp;
+  float *gtile = reinterpret_cast<float *>(base_w);                                   // [2][32 points][32 states]
+  Rec *recs = reinterpret_cast<Rec *>(base_w + 2 * 32 * 32 * sizeof(float));          // [2][34]
+  float *bins = reinterpret_cast<float *>(base_w + 2 * 32 * 32 * sizeof(float) + 2 * 34 * sizeof(Rec));
+  float *bd = bins + lane;
+  char *bdb = reinterpret_cast<char *>(bd);
+  for (int t = 0; t <= Vmax; ++t) bd[t * 32] = 0.f;
+  if (lane < 2) {                                           // the records past a block's end: x = 0, unseen-symbol row
+    recs[32 + lane] = Rec{0.f, 0.f, Vmax * 128, 0};
+    recs[34 + 32 + lane] = Rec{0.f, 0.f, Vmax * 128, 0};
+  }
+
+  Coef<KP> q;
+  Acc<KP> acc;
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    float v[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * kp + h;
+      const bool on = has_c && k < a.tb.K[has_c ? u : 0];
+      const int64_t o = ((int64_t)(has_c ? u : 0) * Kmax + (k < Kmax ? k : 0)) * Npad + j;
+      v[h] = on ? a.tb.gs[o] : 0.f;
+      v[2 + h] = on ? a.tb.gm[o] : 0.f;
+      v[4 + h] = on ? a.tb.gc[o] : -INFINITY;
+    }
+    q.s2[kp] = pk(v[0], v[1]); q.m2[kp] = pk(v[2], v[3]); q.cc2[kp] = pk(v[4], v[5]);
+    acc.S0[kp] = acc.S1[kp] = acc.S2[kp] = 0ull;
+  }
+  // contiguous run of whole blocks per CTA column
+  const int per = (a.nblk + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b0 = (int)blockIdx.x * per;
+  const int b1 = b0 + per < a.nblk ? b0 + per : a.nblk;
+  if (b0 >= b1) return;
+  const float *xcol = a.dv.cont + (int64_t)(has_c ? u : 0) * a.dv.P + a.p0;
+  const uint8_t *dcol = a.dv.disc + (int64_t)(has_d ? u : 0) * a.dv.P + a.p0;
+  const bool gsum_on = u == 0;
+  double gs = 0.0;
+  int inwin = 0;
+
+  // lane l copies, for i = 0..7, the 16 bytes of point 4 i + l / 8, states 4 (l % 8) .. + 3
+  const float *gsrc0 = a.GA + (int64_t)(lane >> 3) * N + blockIdx.y * 32 + (lane & 7) * 4;
+  float *gdst0 = gtile + (lane >> 3) * 32 + (lane & 7) * 4;
+  auto issue_tile = [&](int blk, int stage) {
+    const float *src = gsrc0 + (int64_t)blk * 32 * N;
+    float *dst = gdst0 + stage * 1024;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cp_async16(dst + i * 128, src + (int64_t)i * 4 * N);
+    cp_async_commit();
+  };
+  issue_tile(b0, 0);
+  float xr = has_c ? __ldg(xcol + (int64_t)b0 * 32 + lane) : 0.f;
+  int vr = has_d ? (int)__ldg(dcol + (int64_t)b0 * 32 + lane) : Vmax;
+
+  for (int blk = b0; blk < b1; ++blk) {
+    const int stage = (blk - b0) & 1;
+    Rec *rec = recs + stage * 34;
+    rec[lane] = Rec{xr, xr, (vr < Vmax ? vr : Vmax) * 128, 0};
+    cp_async_wait_all();
+    __syncwarp();
+    if (blk + 1 < b1) {
+      issue_tile(blk + 1, stage ^ 1);
+      if (has_c) xr = __ldg(xcol + (int64_t)(blk + 1) * 32 + lane);
+      if (has_d) vr = (int)__ldg(dcol + (int64_t)(blk + 1) * 32 + lane);
+    }
+    const float *gt = gtile + stage * 1024 + lane;
+    float gsl = 0.f, hmax;
+    if (has_c && has_d) hmax = block32<KP, true, true>(q, acc, gt, rec, bdb, gsl, gsum_on);
+    else if (has_c) hmax = block32<KP, true, false>(q, acc, gt, rec, bdb, gsl, gsum_on);
+    else hmax = block32<KP, false, true>(q, acc, gt, rec, bdb, gsl, gsum_on);
+    gs += (double)gsl;
+    if (has_c && __any_sync(0xffffffffu, hmax > HBIG)) {
+      // rare: a state with posterior mass at a point where fp32 has flushed (part of) its mixture.  Each lane takes
+      // back what its fast path added for such points (same instructions, weight -g) and adds the exponent-shifted
+      // evaluation instead.
+#pragma unroll 1
+      for (int p = 0; p < 32; ++p) {
+        const float x = rec[p].x0, g = gt[p * 32];
+        Pend<KP> pr;
+        stage1<KP>(q, pk(x, x), pr);
+        const float inv = g * rcp_approx(fmaxf(mix_sum<KP>(pr), 1.17549435e-38f));
+        const bool redo = inv > HBIG;
+        stage2<KP>(acc, pr, redo ? -g : 0.f);
+        shifted_point<KP>(q, acc, x, redo ? g : 0.f);
+      }
+    }
+    inwin += 32;
+    if (inwin >= a.window || blk + 1 >= b1) {
+      inwin = 0;
+      if (has_c) {
+        const int K = a.tb.K[u];
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) {
+          float sv[2], mv[2], a0[2], a1[2], a2v[2];
+          unpk(q.s2[kp], sv[0], sv[1]); unpk(q.m2[kp], mv[0], mv[1]);
+          unpk(acc.S0[kp], a0[0], a0[1]); unpk(acc.S1[kp], a1[0], a1[1]); unpk(acc.S2[kp], a2v[0], a2v[1]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = 2 * kp + h;
+            if (k < K && a0[h] != 0.f) {
+              // z = (x - mu') s with mu' = -m/s the fp32-rounded centre; re-centre on the fp64 old mean
+              const int64_t dst = ((int64_t)u * N + j) * Kmax + k;
+              const double s = (double)sv[h];
+              double m0 = (double)a0[h], m1 = 0.0, m2d = 0.0;
+              if (s > 0.0) {
+                const double delta = -(double)mv[h] / s - a.mu_old[dst];
+                const double c1 = (double)a1[h] / s, c2 = (double)a2v[h] / (s * s);
+                m1 = c1 + delta * m0;
+                m2d = c2 + 2.0 * delta * c1 + delta * delta * m0;
+              }
+              atomicAdd(a.gmm + 3 * dst + 0, m0);
+              atomicAdd(a.gmm + 3 * dst + 1, m1);
+              atomicAdd(a.gmm + 3 * dst + 2, m2d);
+            }
+          }
+          acc.S0[kp] = acc.S1[kp] = acc.S2[kp] = 0ull;
+        }
+      }
+      if (gsum_on) {
+        if (gs != 0.0) atomicAdd(a.gsum + j, gs);
+        gs = 0.0;
+      }
+      if (has_d) {
+        for (int v = 0; v < Vmax; ++v) {
+          const float b = bd[v * 32];
+          if (b != 0.f) atomicAdd(a.cat + ((int64_t)u * N + j) * Vmax + v, (double)b);
+          bd[v * 32] = 0.f;
+        }
+        bd[Vmax * 32] = 0.f;                                // unseen-symbol row is discarded
+      }
+    }
+  }
+}
+
+size_t stats2_smem(const Dims &d, int nw) {
+  return (size_t)nw * ((size_t)2 * 32 * 32 * sizeof(float) + 2 * 34 * sizeof(Rec) + (size_t)(d.Vmax + 1) * 32 * sizeof(float));
+}
+
+}  // namespace
+
+bool stats2_supported(const dnbc_ctx *c) {
+  const Dims &d = c->dm;
+  const int units = d.C > d.D ? d.C : d.D;
+  return d.N % 32 == 0 && d.Kmax <= 8 && units >= 1 && stats2_smem(d, NW_MAX) <= 110 * 1024;
+}
+
+// whole 32-point blocks of [p0, p0 + np); returns the number of points covered (the caller gives the rest to k_stats_pk)
+int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
+  const int64_t nblk = np / 32;
+  if (nblk <= 0) return 0;
+  const Dims &d = c->dm;
+  StatsLayout sl = stats_layout(d);
+  const int units = d.C > d.D ? d.C : d.D;
+  // 16 warps per SM at <= 128 registers: CTAs of nw warps, e.g. 3 x 5 warps when there are 5 variables
+  const int nw = units > NW_MAX ? NW_MAX : units;
+  const int gz = (units + nw - 1) / nw, gy = d.N / 32;
+  Stat2Args a{d, c->tables(), c->data(), p0, (int)nblk, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
+              c->d_stats + sl.gamma, 4096, nw};
+  const size_t smem = stats2_smem(d, nw);
+  const int per_sm = 16 / nw > 8 ? 8 : 16 / nw;
+  int64_t gx = (int64_t)c->sm_count * per_sm / ((int64_t)gy * gz);
+  const int64_t maxgx = (nblk + 7) / 8;
+  if (gx > maxgx) gx = maxgx;
+  if (gx < 1) gx = 1;
+  const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
+  const int KP = (d.Kmax + 1) / 2;
+#define STATS2_CASE(KP_)                                                                                          \
+  if (KP == KP_) {                                                                                                \
+    cudaFuncSetAttribute(k_stats2<KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
+    k_stats2<KP_><<<grid, nw * 32, smem, c->stream>>>(a);                                                          \
+  }
+  STATS2_CASE(1) STATS2_CASE(2) STATS2_CASE(3) STATS2_CASE(4)
+#undef STATS2_CASE
+  return nblk * 32;
+}

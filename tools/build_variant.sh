@@ -9,5 +9,5 @@ stem=$(basename $src .cu)
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $flags \
   -c -o $ROOT/build/${stem}_$name.o $ROOT/dnbc_scala_b200/csrc/$src
 objs=$(ls $ROOT/dnbc_scala_b200/lib/*.o | grep -v "/$stem.o")
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/build/libdnbc_$name.so $objs $ROOT/build/${stem}_$name.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/build/libdnbc_$name.so $objs $ROOT/build/${stem}_$name.o -lcudart -lnccl
 echo built build/libdnbc_$name.so
