@@ -585,6 +585,10 @@ static int estep_chunks(dnbc_ctx *c, int clamp_labels, const std::vector<Chunk> 
       if (rc) return rc;
     }
     if (ready) CU_TRY(c, cudaStreamWaitEvent(c->stream, (*ready)[k], 0));
+    if (!clamp_labels && fused_estep_wanted(c, ch.s1 - ch.s0)) {   // N <= 16, few sequences: the whole E-step in one launch (k_fused.cu)
+      launch_estep_fused(c, ch.s0, ch.s1, ch.p0);
+      continue;
+    }
     launch_emission_f32(c, ch.p0, ch.np, c->E);
     if (clamp_labels) launch_clamp_labels(c, ch.p0, ch.np, c->E);
     launch_forward(c, ch.s0, ch.s1, ch.p0);
@@ -721,6 +725,10 @@ extern "C" int dnbc_set_option(dnbc_ctx *c, int option, int64_t value) {
       return DNBC_OK;
     case DNBC_OPT_FB2_INTERLEAVE:
       c->opt_fb2_interleave = value != 0;
+      return DNBC_OK;
+    case DNBC_OPT_FUSED_ESTEP:
+      if (value < 0 || value > 2) return dnbc_fail(c, DNBC_EINVAL, "set_option: fused E-step mode must be 0, 1 or 2");
+      c->opt_fused_estep = (int)value;
       return DNBC_OK;
     default:
       return dnbc_fail(c, DNBC_EINVAL, "set_option: unknown option %d", option);

@@ -119,6 +119,7 @@ struct dnbc_ctx {
   // dnbc_set_option
   int64_t opt_max_chunk_points = 0;   // 0 = sized from the free memory
   bool opt_fb2_interleave = false;    // keep the four-sequences-per-lane-group recursions on small inputs
+  int opt_fused_estep = 0;            // 0 auto, 1 always (when it fits), 2 never
 
   // library-owned NCCL communicator (dnbc_comm.cu); void* keeps nccl.h out of the kernel files
   void *comm = nullptr;
@@ -183,6 +184,9 @@ bool mixture_stats_fast(const dnbc_ctx *c);
 void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out);
 void launch_mixture_stats(dnbc_ctx *c, int64_t p0, int64_t np);
 bool stats2_supported(const dnbc_ctx *c);
+bool fused_estep_supported(const dnbc_ctx *c);
+bool fused_estep_wanted(const dnbc_ctx *c, int64_t n_seq);
+void launch_estep_fused(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0);
 int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np);
 bool fb3_supported(const dnbc_ctx *c);
 void launch_fb3(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);

@@ -354,3 +354,82 @@ def test_c_abi_smoke_program():
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "dnbc_scala_b200", "lib") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# ---------------------------------------------------------------------------------
+# N <= 16: the single-launch E-step (k_fused.cu) and the general pipeline, both forced
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,V,K,lengths", [
+    (10, [10] * 5, [3, 1, 4, 2, 3], [200] * 9 + [37, 1, 0, 150]),      # config-1 variables, ragged, an empty sequence
+    (12, [4], [], [200] * 7 + [3]),                                    # toy robot: discrete only
+    (10, [], [3] * 5, [200] * 8),                                      # config-3 shape
+    (1, [3], [2], [5, 1, 9]),                                          # a single state
+    (3, [2, 2], [8], [40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50]),    # ten groups of three lanes, K = 8
+    (7, [5], [5, 7], [64] * 6),                                        # odd N (zero pad entry), odd K
+    (16, [6], [2], [90] * 5),                                          # the largest state count the kernel takes
+])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fused_and_general_estep_match_oracle(oracle, N, V, K, lengths, mode):
+    """dnbc_set_option(DNBC_OPT_FUSED_ESTEP): 1 forces the single-launch kernel, 2 the general pipeline;
+    both against the fp64 oracle -- statistics, log-likelihood and three EM iterations."""
+    m = random_model(oracle, N, V, K, 400 + N, transitions_per_state=min(N, 6))
+    data = sample(oracle, m, lengths, 410 + N)
+    q = perturb(oracle, m, 420 + N)
+    want = oracle.estep(q, data)
+    w3 = q.copy()
+    ll_want = oracle.em_iterate(w3, data, 3)
+    with ctx_for(nat, q) as ctx:
+        ctx.set_option(nat.OPT_FUSED_ESTEP, mode)
+        upload(ctx, data, labels=False, dtype=np.float32)
+        l0 = ctx.launch_count()
+        ctx.em_estep()
+        launches = ctx.launch_count() - l0
+        got = ctx.em_get_stats()
+        ll = ctx.em_iterate(3)
+        p = ctx.get_params()
+    assert launches == 1 if mode == 1 else launches >= 4, launches     # one launch for the whole E-step vs the pipeline
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    for key in ("pi", "xi", "gamma", "cat"):
+        np.testing.assert_allclose(sg[key], sw[key], rtol=1e-4, atol=1e-4, err_msg=key)
+    if K:
+        np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=1e-4, atol=1e-3, err_msg="gmm s0")
+        np.testing.assert_allclose(sg["gmm"][..., 1], sw["gmm"][..., 1], rtol=1e-4, atol=2e-3 * np.sqrt(data.P), err_msg="gmm s1")
+        np.testing.assert_allclose(sg["gmm"][..., 2], sw["gmm"][..., 2], rtol=1e-4, atol=1e-2 * np.sqrt(data.P), err_msg="gmm s2")
+    np.testing.assert_allclose(ll, ll_want, rtol=TOL)
+    np.testing.assert_allclose(p["A"], w3.A, rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(p["B"], w3.B, rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(p["mu"], w3.mu, rtol=5e-4, atol=5e-4)
+
+
+def test_fused_estep_outliers_and_long_sequences(oracle):
+    """The fused kernel's exponent-shifted paths (points 15-25 sigma from every component) and its refusal of
+    sequences whose rows do not fit shared memory (T = 4000 at N = 16 falls back to the general pipeline)."""
+    m = random_model(oracle, 6, [5], [3, 2], 471)
+    m.var[0, :, :3] = 4.0
+    data = sample(oracle, m, [40] * 12 + [7, 1], 472)
+    rng = np.random.default_rng(473)
+    hit = rng.choice(data.P, size=37, replace=False)
+    data.cont[0, hit] = rng.choice([-1.0, 1.0], 37) * rng.uniform(60, 90, 37)
+    data = oracle.Data(data.off, data.disc, data.cont, data.labels)
+    want = oracle.split_stats(m, oracle.estep(m, data))
+    for mode in (1, 2):
+        with ctx_for(nat, m) as ctx:
+            ctx.set_option(nat.OPT_FUSED_ESTEP, mode)
+            upload(ctx, data, labels=False, dtype=np.float32)
+            ctx.em_estep()
+            got = oracle.split_stats(m, ctx.em_get_stats())
+        assert np.isfinite(got["ll"]) and abs(got["ll"] - want["ll"]) <= TOL * abs(want["ll"]), mode
+        np.testing.assert_allclose(got["gamma"], want["gamma"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(got["gmm"][..., 0], want["gmm"][..., 0], rtol=1e-4, atol=1e-3)
+    m2 = random_model(oracle, 16, [3], [1], 481, transitions_per_state=4)
+    long = sample(oracle, m2, [4000, 10], 482)
+    w2 = oracle.split_stats(m2, oracle.estep(m2, long))
+    with ctx_for(nat, m2) as ctx:
+        ctx.set_option(nat.OPT_FUSED_ESTEP, 1)              # asked for, but 2 x 4000 x 16 floats do not fit: general path
+        upload(ctx, long, labels=False, dtype=np.float32)
+        l0 = ctx.launch_count()
+        ctx.em_estep()
+        assert ctx.launch_count() - l0 >= 4
+        g2 = oracle.split_stats(m2, ctx.em_get_stats())
+    assert abs(g2["ll"] - w2["ll"]) <= TOL * abs(w2["ll"])

@@ -1,5 +1,5 @@
 """Per-kernel-family timings of one EM iteration for A/B library builds.
-usage: DNBC_B200_LIB=build/libdnbc_x.so python tools/kbench.py [workload] [seqs] [iters]"""
+usage: DNBC_B200_LIB=build/libdnbc_x.so python tools/kbench.py [workload] [seqs] [iters] [fused mode 0|1|2]"""
 import json
 import os
 import sys
@@ -14,6 +14,8 @@ iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 truth = workloads.true_params(wl)
 init = workloads.perturbed_params(wl, truth)
 ctx = nat.Context(wl.N, [wl.V] * wl.D, [wl.K] * wl.C, device=0)
+if len(sys.argv) > 4:
+    ctx.set_option(nat.OPT_FUSED_ESTEP, int(sys.argv[4]))      # 1 = fused E-step kernel, 2 = general pipeline
 ctx.set_params(truth["pi"], truth["A"], truth["B"], truth["w"], truth["mu"], truth["var"])
 ctx.generate(seqs, wl.T, 20260000 + wl.index * 1000)
 ctx.set_params(init["pi"], init["A"], init["B"], init["w"], init["mu"], init["var"])
