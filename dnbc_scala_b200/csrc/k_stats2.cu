@@ -69,9 +69,15 @@ template <int KP>
 struct Acc {
   u64 S0[KP], S1[KP], S2[KP];    // sum r, sum r z, sum r z^2 over the current window
 };
+#ifndef S2_TTRICK
+#define S2_TTRICK 1
+#endif
 template <int KP>
 struct Pend {
   u64 z[KP], e[KP];
+#if S2_TTRICK
+  u64 a[KP];                     // exponent arguments c' - z^2 (see stage2)
+#endif
 };
 
 // stage 1 of a point: standardised coordinate and the 2 KP exponentials
@@ -80,7 +86,12 @@ __device__ __forceinline__ void stage1(const Coef<KP> &q, u64 xx, Pend<KP> &n) {
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     n.z[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
+#if S2_TTRICK
+    n.a[kp] = fnma2(n.z[kp], n.z[kp], q.cc2[kp]);
+    n.e[kp] = ex2_2(n.a[kp]);
+#else
     n.e[kp] = ex2_2(fnma2(n.z[kp], n.z[kp], q.cc2[kp]));
+#endif
   }
 }
 // mixture sum of a pending point (the underflow decision is taken on exactly this value, here and in the redo)
@@ -107,9 +118,16 @@ __device__ __forceinline__ float stage2(Acc<KP> &a, const Pend<KP> &p, float g) 
   for (int kp = 0; kp < KP; ++kp) {
     const u64 rr = mul2(p.e[kp], inv2);
     a.S0[kp] = add2(a.S0[kp], rr);
+#if S2_TTRICK
+    // z^2 = c' - arg, so sum r z^2 = c' S0 - sum r arg: the second moment costs one FMA on the argument the
+    // exponential was taken of (a.S2 holds sum r arg here; the flush converts)
+    a.S1[kp] = fma2(rr, p.z[kp], a.S1[kp]);
+    a.S2[kp] = fma2(rr, p.a[kp], a.S2[kp]);
+#else
     const u64 rz = mul2(rr, p.z[kp]);
     a.S1[kp] = add2(a.S1[kp], rz);
     a.S2[kp] = fma2(rz, p.z[kp], a.S2[kp]);
+#endif
   }
   return inv;
 }
@@ -129,22 +147,27 @@ __device__ __forceinline__ void shifted_point(const Coef<KP> &q, Acc<KP> &a, flo
   }
   mx = mx == -INFINITY ? 0.f : mx;
   const u64 nm = pk(-mx, -mx);
-  u64 sum2 = 0ull;
+  u64 sum2 = 0ull, e2[KP];
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
-    a2[kp] = ex2_2(add2(a2[kp], nm));
-    sum2 = add2(sum2, a2[kp]);
+    e2[kp] = ex2_2(add2(a2[kp], nm));
+    sum2 = add2(sum2, e2[kp]);
   }
   const float sum = hsum(sum2);
   const float inv = sum > 0.f ? g * rcp_approx(sum) : 0.f;
   const u64 inv2 = pk(inv, inv);
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
-    const u64 rr = mul2(a2[kp], inv2);
+    const u64 rr = mul2(e2[kp], inv2);
     a.S0[kp] = add2(a.S0[kp], rr);
+#if S2_TTRICK
+    a.S1[kp] = fma2(rr, z2[kp], a.S1[kp]);
+    a.S2[kp] = fma2(rr, a2[kp], a.S2[kp]);                  // (the unshifted argument, as in stage2)
+#else
     const u64 rz = mul2(rr, z2[kp]);
     a.S1[kp] = add2(a.S1[kp], rz);
     a.S2[kp] = fma2(rz, z2[kp], a.S2[kp]);
+#endif
   }
 }
 
@@ -219,6 +242,21 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
 
   Coef<KP> q;
   Acc<KP> acc;
+#if S2_TTRICK
+  // Responsibilities do not change when every component of a mixture is scaled by the same factor, so the log2
+  // constants are shifted per (variable, state) to put the largest at CREF = E[z^2] of a well-fitted component:
+  // the arguments c' - z^2 that the second moment is accumulated through (stage2) then average near zero for the
+  // components that carry the mass, and c' S0 - sum r arg loses at most a bit to cancellation.  Components
+  // without mass (padding, zero weights) get a finite constant far below the fp32 exponent range: 0 * (-inf) would be NaN.
+  constexpr float CREF = 0.72134752f, CNONE = -20000.f;
+  float kappa = 0.f;
+  {
+    float cmax = -INFINITY;
+    for (int k = 0; k < Kmax; ++k)
+      if (has_c && k < a.tb.K[u]) cmax = fmaxf(cmax, a.tb.gc[((int64_t)u * Kmax + k) * Npad + j]);
+    kappa = cmax == -INFINITY ? 0.f : CREF - cmax;
+  }
+#endif
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     float v[6];
@@ -229,7 +267,11 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
       const int64_t o = ((int64_t)(has_c ? u : 0) * Kmax + (k < Kmax ? k : 0)) * Npad + j;
       v[h] = on ? a.tb.gs[o] : 0.f;
       v[2 + h] = on ? a.tb.gm[o] : 0.f;
+#if S2_TTRICK
+      v[4 + h] = on ? fmaxf(a.tb.gc[o] + kappa, CNONE) : CNONE;
+#else
       v[4 + h] = on ? a.tb.gc[o] : -INFINITY;
+#endif
     }
     q.s2[kp] = pk(v[0], v[1]); q.m2[kp] = pk(v[2], v[3]); q.cc2[kp] = pk(v[4], v[5]);
     acc.S0[kp] = acc.S1[kp] = acc.S2[kp] = 0ull;
@@ -298,8 +340,8 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
         const int K = a.tb.K[u];
 #pragma unroll
         for (int kp = 0; kp < KP; ++kp) {
-          float sv[2], mv[2], a0[2], a1[2], a2v[2];
-          unpk(q.s2[kp], sv[0], sv[1]); unpk(q.m2[kp], mv[0], mv[1]);
+          float sv[2], mv[2], cv[2], a0[2], a1[2], a2v[2];
+          unpk(q.s2[kp], sv[0], sv[1]); unpk(q.m2[kp], mv[0], mv[1]); unpk(q.cc2[kp], cv[0], cv[1]);
           unpk(acc.S0[kp], a0[0], a0[1]); unpk(acc.S1[kp], a1[0], a1[1]); unpk(acc.S2[kp], a2v[0], a2v[1]);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -311,7 +353,12 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
               double m0 = (double)a0[h], m1 = 0.0, m2d = 0.0;
               if (s > 0.0) {
                 const double delta = -(double)mv[h] / s - a.mu_old[dst];
-                const double c1 = (double)a1[h] / s, c2 = (double)a2v[h] / (s * s);
+#if S2_TTRICK
+                const double zz = (double)cv[h] * (double)a0[h] - (double)a2v[h];   // sum r z^2 = c' S0 - sum r arg
+#else
+                const double zz = (double)a2v[h];
+#endif
+                const double c1 = (double)a1[h] / s, c2 = zz / (s * s);
                 m1 = c1 + delta * m0;
                 m2d = c2 + 2.0 * delta * c1 + delta * delta * m0;
               }

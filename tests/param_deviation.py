@@ -7,7 +7,7 @@ def rel(a,b,floor):
     a=np.asarray(a); b=np.asarray(b)
     m=np.abs(b)>floor
     return float(np.max(np.abs(a[m]-b[m])/np.abs(b[m]))) if m.any() else 0.0
-for (N,V,K,S,T) in [(10,[10]*5,[3,1,4,2,3],64,200),(12,[4],[],48,200),(10,[],[3]*5,64,200),(64,[10]*4,[8]*4,24,200)]:
+for (N,V,K,S,T) in [(10,[10]*5,[3,1,4,2,3],64,200),(12,[4],[],48,200),(10,[],[3]*5,64,200),(64,[10]*4,[8]*4,24,200),(64,[10]*2,[8]*4,96,1000),(64,[],[8,3,5],256,500)]:
     m = random_model(oracle, N, V, K, 61, unit_var=False)
     data = sample(oracle, m, [T]*S, 62)
     q = perturb(oracle, m, 63)
