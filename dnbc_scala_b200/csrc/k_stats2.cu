@@ -41,6 +41,7 @@ struct Stat2Args {
   double *gmm, *cat, *gsum;
   int window;                    // points per fp32 accumulation window (multiple of 32)
   int nw;                        // warps per CTA
+  int LG, PG;                    // grouped layout (N <= 32): lanes per point, points per warp step (32 / LG)
 };
 
 __device__ __forceinline__ u64 ex2_2(u64 a) {
@@ -179,9 +180,12 @@ struct alignas(16) Rec { float x0, x1; int voff; int pad; };
 // observation records, bdb = this lane's histogram column as a byte address (rows are 128 bytes apart and the
 // record carries 128 * symbol).  Four points per loop trip with constant offsets from two bumped pointers; the two
 // pipeline buffers alternate, so nothing is copied between points.  Returns the largest weight g / sum seen.
-template <int KP, bool HAS_C, bool HAS_D>
+// GRP (state counts up to 32): a warp step covers PG points x LG lanes, so a block is 32 steps = 32 PG points; gstep /
+// rstep are the distances between consecutive steps in the posterior tile (floats) and the record array.
+template <int KP, bool HAS_C, bool HAS_D, bool GRP>
 __device__ __forceinline__ float block32(const Coef<KP> &q, Acc<KP> &acc, const float *gt, const Rec *rec, char *bdb, float &gsl,
-                                         bool gsum_on) {
+                                         bool gsum_on, int gstep_, int rstep_) {
+  const int gstep = GRP ? gstep_ : 32, rstep = GRP ? rstep_ : 1;
   float hmax = 0.f;
   Pend<KP> pa, pb;
   if (HAS_C) {
@@ -190,21 +194,21 @@ __device__ __forceinline__ float block32(const Coef<KP> &q, Acc<KP> &acc, const 
   }
   const float4 *rp = reinterpret_cast<const float4 *>(rec);
 #pragma unroll 1
-  for (int it = 0; it < 32 / S2_PTS; ++it, rp += S2_PTS, gt += 32 * S2_PTS) {
+  for (int it = 0; it < 32 / S2_PTS; ++it, rp += S2_PTS * rstep, gt += gstep * S2_PTS) {
 #pragma unroll
     for (int h = 0; h < S2_PTS; h += 2) {
-      const float g0 = gt[32 * h], g1 = gt[32 * h + 32];
+      const float g0 = gt[gstep * h], g1 = gt[gstep * h + gstep];
       if (HAS_C) {
-        const float2 x1 = *reinterpret_cast<const float2 *>(rp + h + 1);
+        const float2 x1 = *reinterpret_cast<const float2 *>(rp + (h + 1) * rstep);
         stage1<KP>(q, pk(x1.x, x1.y), pb);
         hmax = fmaxf(hmax, stage2<KP>(acc, pa, g0));
-        const float2 x2 = *reinterpret_cast<const float2 *>(rp + h + 2);
+        const float2 x2 = *reinterpret_cast<const float2 *>(rp + (h + 2) * rstep);
         stage1<KP>(q, pk(x2.x, x2.y), pa);
         hmax = fmaxf(hmax, stage2<KP>(acc, pb, g1));
       }
       if (HAS_D) {
         // categorical histogram: bins[symbol][state] += gamma
-        const int v0 = __float_as_int(rp[h].z), v1 = __float_as_int(rp[h + 1].z);
+        const int v0 = __float_as_int(rp[h * rstep].z), v1 = __float_as_int(rp[(h + 1) * rstep].z);
         *reinterpret_cast<float *>(bdb + v0) += g0;
         *reinterpret_cast<float *>(bdb + v1) += g1;
       }
@@ -217,28 +221,43 @@ __device__ __forceinline__ float block32(const Coef<KP> &q, Acc<KP> &acc, const 
 #ifndef S2_MAXREG
 #define S2_MAXREG 128
 #endif
-template <int KP>
+constexpr int PGMAX = 4;         // points per warp step in the grouped layout (N >= 8)
+
+// GRP = false: N a multiple of 32; blockIdx.y selects a 32-state slice, a block is 32 points, the posterior tile is
+//              the [32 points][32 states] slice of GA.
+// GRP = true : N <= 32; lane = (point slot gi, state lj), a block is 32 steps of PG points, the tile is the contiguous
+//              [32 PG points][N] piece of GA.  Lanes past the last whole group and padded states carry zero weight.
+template <int KP, bool GRP>
 __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.y * 32 + lane;                     // always a real state (N % 32 == 0)
+  const int LG = GRP ? a.LG : 32, PG = GRP ? a.PG : 1;
+  const int gi = GRP ? lane / LG : 0, lj = GRP ? lane % LG : lane;
+  const bool lane_on = !GRP || (gi < PG && lj < N);
+  const int j = GRP ? (lane_on ? lj : 0) : blockIdx.y * 32 + lane;   // a real state
   const int u = blockIdx.z * a.nw + w;                      // this warp's variable index
   const bool has_c = u < C, has_d = u < D;
   if (!has_c && !has_d) return;
+  const int TPB = 32 * PG;                                  // points per block
+  const int tile_floats = GRP ? TPB * N : 32 * 32;
+  const int nrec = TPB + PG + 1;                            // (the pipeline reads one step past the block)
   const int bin_floats = (Vmax + 1) * 32;
-  const size_t per_warp = (size_t)2 * 32 * 32 * sizeof(float) + 2 * 34 * sizeof(Rec) + (size_t)bin_floats * sizeof(float);
+  const size_t per_warp = (size_t)2 * tile_floats * sizeof(float) + (size_t)2 * nrec * sizeof(Rec) + (size_t)(bin_floats + 4) * sizeof(float);
   unsigned char *base_w = smem_raw + (size_t)w * per_warp;
-  float *gtile = reinterpret_cast<float *>(base_w);                                   // [2][32 points][32 states]
-  Rec *recs = reinterpret_cast<Rec *>(base_w + 2 * 32 * 32 * sizeof(float));          // [2][34]
-  float *bins = reinterpret_cast<float *>(base_w + 2 * 32 * 32 * sizeof(float) + 2 * 34 * sizeof(Rec));
+  float *gtile = reinterpret_cast<float *>(base_w);                                   // [2][tile_floats]
+  Rec *recs = reinterpret_cast<Rec *>(base_w + (size_t)2 * tile_floats * sizeof(float));   // [2][nrec]
+  float *bins = reinterpret_cast<float *>(base_w + (size_t)2 * tile_floats * sizeof(float) + (size_t)2 * nrec * sizeof(Rec));
   float *bd = bins + lane;
   char *bdb = reinterpret_cast<char *>(bd);
   for (int t = 0; t <= Vmax; ++t) bd[t * 32] = 0.f;
-  if (lane < 2) {                                           // the records past a block's end: x = 0, unseen-symbol row
-    recs[32 + lane] = Rec{0.f, 0.f, Vmax * 128, 0};
-    recs[34 + 32 + lane] = Rec{0.f, 0.f, Vmax * 128, 0};
+  if (lane <= PG) {                                         // the records past a block's end: x = 0, unseen-symbol row
+    recs[TPB + lane] = Rec{0.f, 0.f, Vmax * 128, 0};
+    recs[nrec + TPB + lane] = Rec{0.f, 0.f, Vmax * 128, 0};
   }
+  // (grouped layout: a zero word at the end of the warp's shared memory for lanes without a state)
+  float *zero_word = bins + bin_floats;
+  if (GRP && lane == 0) *zero_word = 0.f;
 
   Coef<KP> q;
   Acc<KP> acc;
@@ -253,7 +272,7 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   {
     float cmax = -INFINITY;
     for (int k = 0; k < Kmax; ++k)
-      if (has_c && k < a.tb.K[u]) cmax = fmaxf(cmax, a.tb.gc[((int64_t)u * Kmax + k) * Npad + j]);
+      if (has_c && lane_on && k < a.tb.K[u]) cmax = fmaxf(cmax, a.tb.gc[((int64_t)u * Kmax + k) * Npad + j]);
     kappa = cmax == -INFINITY ? 0.f : CREF - cmax;
   }
 #endif
@@ -263,7 +282,7 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int k = 2 * kp + h;
-      const bool on = has_c && k < a.tb.K[has_c ? u : 0];
+      const bool on = has_c && lane_on && k < a.tb.K[has_c ? u : 0];
       const int64_t o = ((int64_t)(has_c ? u : 0) * Kmax + (k < Kmax ? k : 0)) * Npad + j;
       v[h] = on ? a.tb.gs[o] : 0.f;
       v[2 + h] = on ? a.tb.gm[o] : 0.f;
@@ -287,36 +306,69 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   double gs = 0.0;
   int inwin = 0;
 
-  // lane l copies, for i = 0..7, the 16 bytes of point 4 i + l / 8, states 4 (l % 8) .. + 3
+  // posterior tile of a block.  !GRP: lane l copies, for i = 0..7, the 16 bytes of point 4 i + l / 8, states
+  // 4 (l % 8) .. + 3 of this slice.  GRP: the tile is one contiguous piece of GA.
   const float *gsrc0 = a.GA + (int64_t)(lane >> 3) * N + blockIdx.y * 32 + (lane & 7) * 4;
   float *gdst0 = gtile + (lane >> 3) * 32 + (lane & 7) * 4;
   auto issue_tile = [&](int blk, int stage) {
-    const float *src = gsrc0 + (int64_t)blk * 32 * N;
-    float *dst = gdst0 + stage * 1024;
+    if (GRP) {
+      const float *src = a.GA + (int64_t)blk * tile_floats;
+      float *dst = gtile + stage * tile_floats;
+      for (int c = lane * 4; c < tile_floats; c += 128) cp_async16(dst + c, src + c);
+    } else {
+      const float *src = gsrc0 + (int64_t)blk * 32 * N;
+      float *dst = gdst0 + stage * 1024;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cp_async16(dst + i * 128, src + (int64_t)i * 4 * N);
+      for (int i = 0; i < 8; ++i) cp_async16(dst + i * 128, src + (int64_t)i * 4 * N);
+    }
     cp_async_commit();
   };
   issue_tile(b0, 0);
-  float xr = has_c ? __ldg(xcol + (int64_t)b0 * 32 + lane) : 0.f;
-  int vr = has_d ? (int)__ldg(dcol + (int64_t)b0 * 32 + lane) : Vmax;
+  float xr[GRP ? PGMAX : 1];
+  int vr[GRP ? PGMAX : 1];
+  auto load_obs = [&](int blk) {
+    if (GRP) {
+#pragma unroll
+      for (int i = 0; i < PGMAX; ++i) {
+        if (i < PG) {
+          const int64_t pnt = (int64_t)blk * TPB + i * 32 + lane;
+          xr[i] = has_c ? __ldg(xcol + pnt) : 0.f;
+          vr[i] = has_d ? (int)__ldg(dcol + pnt) : Vmax;
+        }
+      }
+    } else {
+      if (has_c) xr[0] = __ldg(xcol + (int64_t)blk * 32 + lane);
+      if (has_d) vr[0] = (int)__ldg(dcol + (int64_t)blk * 32 + lane);
+    }
+  };
+  xr[0] = 0.f;
+  vr[0] = Vmax;
+  load_obs(b0);
 
   for (int blk = b0; blk < b1; ++blk) {
     const int stage = (blk - b0) & 1;
-    Rec *rec = recs + stage * 34;
-    rec[lane] = Rec{xr, xr, (vr < Vmax ? vr : Vmax) * 128, 0};
+    Rec *rec = recs + stage * nrec;
+    if (GRP) {
+#pragma unroll
+      for (int i = 0; i < PGMAX; ++i)
+        if (i < PG) rec[i * 32 + lane] = Rec{xr[i], xr[i], (vr[i] < Vmax ? vr[i] : Vmax) * 128, 0};
+    } else {
+      rec[lane] = Rec{xr[0], xr[0], (vr[0] < Vmax ? vr[0] : Vmax) * 128, 0};
+    }
     cp_async_wait_all();
     __syncwarp();
     if (blk + 1 < b1) {
       issue_tile(blk + 1, stage ^ 1);
-      if (has_c) xr = __ldg(xcol + (int64_t)(blk + 1) * 32 + lane);
-      if (has_d) vr = (int)__ldg(dcol + (int64_t)(blk + 1) * 32 + lane);
+      load_obs(blk + 1);
     }
-    const float *gt = gtile + stage * 1024 + lane;
+    // this lane's column of the tile and its first record; lanes without a state read a zero word with stride 0
+    const float *gt = GRP ? (lane_on ? gtile + stage * tile_floats + gi * N + lj : zero_word) : gtile + stage * 1024 + lane;
+    const int gstep = GRP ? (lane_on ? PG * N : 0) : 32;
+    const Rec *rec0 = rec + (GRP ? (gi < PG ? gi : 0) : 0);
     float gsl = 0.f, hmax;
-    if (has_c && has_d) hmax = block32<KP, true, true>(q, acc, gt, rec, bdb, gsl, gsum_on);
-    else if (has_c) hmax = block32<KP, true, false>(q, acc, gt, rec, bdb, gsl, gsum_on);
-    else hmax = block32<KP, false, true>(q, acc, gt, rec, bdb, gsl, gsum_on);
+    if (has_c && has_d) hmax = block32<KP, true, true, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
+    else if (has_c) hmax = block32<KP, true, false, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
+    else hmax = block32<KP, false, true, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
     gs += (double)gsl;
     if (has_c && __any_sync(0xffffffffu, hmax > HBIG)) {
       // rare: a state with posterior mass at a point where fp32 has flushed (part of) its mixture.  Each lane takes
@@ -324,7 +376,7 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
       // evaluation instead.
 #pragma unroll 1
       for (int p = 0; p < 32; ++p) {
-        const float x = rec[p].x0, g = gt[p * 32];
+        const float x = rec0[p * PG].x0, g = gt[p * gstep];
         Pend<KP> pr;
         stage1<KP>(q, pk(x, x), pr);
         const float inv = g * rcp_approx(fmaxf(mix_sum<KP>(pr), 1.17549435e-38f));
@@ -333,10 +385,10 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
         shifted_point<KP>(q, acc, x, redo ? g : 0.f);
       }
     }
-    inwin += 32;
+    inwin += TPB;
     if (inwin >= a.window || blk + 1 >= b1) {
       inwin = 0;
-      if (has_c) {
+      if (has_c && lane_on) {
         const int K = a.tb.K[u];
 #pragma unroll
         for (int kp = 0; kp < KP; ++kp) {
@@ -367,17 +419,18 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
               atomicAdd(a.gmm + 3 * dst + 2, m2d);
             }
           }
-          acc.S0[kp] = acc.S1[kp] = acc.S2[kp] = 0ull;
         }
       }
+#pragma unroll
+      for (int kp = 0; kp < KP; ++kp) acc.S0[kp] = acc.S1[kp] = acc.S2[kp] = 0ull;
       if (gsum_on) {
-        if (gs != 0.0) atomicAdd(a.gsum + j, gs);
+        if (lane_on && gs != 0.0) atomicAdd(a.gsum + j, gs);
         gs = 0.0;
       }
       if (has_d) {
         for (int v = 0; v < Vmax; ++v) {
           const float b = bd[v * 32];
-          if (b != 0.f) atomicAdd(a.cat + ((int64_t)u * N + j) * Vmax + v, (double)b);
+          if (lane_on && b != 0.f) atomicAdd(a.cat + ((int64_t)u * N + j) * Vmax + v, (double)b);
           bd[v * 32] = 0.f;
         }
         bd[Vmax * 32] = 0.f;                                // unseen-symbol row is discarded
@@ -386,8 +439,20 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   }
 }
 
-size_t stats2_smem(const Dims &d, int nw) {
-  return (size_t)nw * ((size_t)2 * 32 * 32 * sizeof(float) + 2 * 34 * sizeof(Rec) + (size_t)(d.Vmax + 1) * 32 * sizeof(float));
+// lane groups of the grouped layout: the state count itself when that packs more points into a warp step
+void group_shape(const Dims &d, int &LG, int &PG) {
+  if (d.N > 16) { LG = 32; PG = 1; return; }
+  const int pg_pad = 32 / d.Npad, pg_exact = 32 / d.N;
+  LG = pg_exact > pg_pad ? d.N : d.Npad;
+  PG = 32 / LG;
+}
+
+size_t stats2_smem(const Dims &d, int nw, bool grp) {
+  int LG = 32, PG = 1;
+  if (grp) group_shape(d, LG, PG);
+  const size_t tile = grp ? (size_t)32 * PG * d.N : 1024;
+  const size_t per_warp = 2 * tile * sizeof(float) + (size_t)2 * (32 * PG + PG + 1) * sizeof(Rec) + (size_t)((d.Vmax + 1) * 32 + 4) * sizeof(float);
+  return (size_t)nw * per_warp;
 }
 
 }  // namespace
@@ -395,22 +460,29 @@ size_t stats2_smem(const Dims &d, int nw) {
 bool stats2_supported(const dnbc_ctx *c) {
   const Dims &d = c->dm;
   const int units = d.C > d.D ? d.C : d.D;
-  return d.N % 32 == 0 && d.Kmax <= 8 && units >= 1 && stats2_smem(d, NW_MAX) <= 110 * 1024;
+  if (d.Kmax > 8 || units < 1) return false;
+  if (d.N % 32 == 0) return stats2_smem(d, NW_MAX, false) <= 110 * 1024;
+  return d.N >= 8 && d.N < 32 && stats2_smem(d, NW_MAX, true) <= 110 * 1024;
 }
 
-// whole 32-point blocks of [p0, p0 + np); returns the number of points covered (the caller gives the rest to k_stats_pk)
+// whole blocks of [p0, p0 + np) (32 points, or 32 warp steps of the grouped layout); returns the number of points
+// covered (the caller gives the rest to k_stats_pk)
 int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
-  const int64_t nblk = np / 32;
-  if (nblk <= 0) return 0;
   const Dims &d = c->dm;
+  const bool grp = d.N % 32 != 0;
+  int LG = 32, PG = 1;
+  if (grp) group_shape(d, LG, PG);
+  const int TPB = 32 * PG;
+  const int64_t nblk = np / TPB;
+  if (nblk <= 0) return 0;
   StatsLayout sl = stats_layout(d);
   const int units = d.C > d.D ? d.C : d.D;
   // 16 warps per SM at <= 128 registers: CTAs of nw warps, e.g. 3 x 5 warps when there are 5 variables
   const int nw = units > NW_MAX ? NW_MAX : units;
-  const int gz = (units + nw - 1) / nw, gy = d.N / 32;
+  const int gz = (units + nw - 1) / nw, gy = grp ? 1 : d.N / 32;
   Stat2Args a{d, c->tables(), c->data(), p0, (int)nblk, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
-              c->d_stats + sl.gamma, 4096, nw};
-  const size_t smem = stats2_smem(d, nw);
+              c->d_stats + sl.gamma, 4096, nw, LG, PG};
+  const size_t smem = stats2_smem(d, nw, grp);
   const int per_sm = 16 / nw > 8 ? 8 : 16 / nw;
   int64_t gx = (int64_t)c->sm_count * per_sm / ((int64_t)gy * gz);
   const int64_t maxgx = (nblk + 7) / 8;
@@ -420,10 +492,15 @@ int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
   const int KP = (d.Kmax + 1) / 2;
 #define STATS2_CASE(KP_)                                                                                          \
   if (KP == KP_) {                                                                                                \
-    cudaFuncSetAttribute(k_stats2<KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
-    k_stats2<KP_><<<grid, nw * 32, smem, c->stream>>>(a);                                                          \
+    if (grp) {                                                                                                    \
+      cudaFuncSetAttribute(k_stats2<KP_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+      k_stats2<KP_, true><<<grid, nw * 32, smem, c->stream>>>(a);                                                  \
+    } else {                                                                                                      \
+      cudaFuncSetAttribute(k_stats2<KP_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+      k_stats2<KP_, false><<<grid, nw * 32, smem, c->stream>>>(a);                                                 \
+    }                                                                                                             \
   }
   STATS2_CASE(1) STATS2_CASE(2) STATS2_CASE(3) STATS2_CASE(4)
 #undef STATS2_CASE
-  return nblk * 32;
+  return nblk * TPB;
 }
