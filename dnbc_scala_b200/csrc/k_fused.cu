@@ -690,9 +690,11 @@ FusedPlan fused_plan(const dnbc_ctx *c) {
 bool fused_estep_supported(const dnbc_ctx *c) { return fused_plan(c).smem != 0; }
 
 // One warp per scheduler exposes every latency, so the fused kernel wins where the general pipeline's five launches
-// are latency-bound themselves -- up to about one and a half waves of sequence batches: 1.1x (README set, 1000
-// sequences) to 1.75x (toy robot, 200 sequences) -- and loses to it on throughput beyond (measured on the B200 over
-// 250 .. 16,000 sequences of three shapes, profiles/r02h_fused_crossover.jsonl).
+// are latency-bound themselves and loses to it on throughput beyond.  The choice compares two fitted costs (B200,
+// 250 .. 16,000 sequences of three shapes, profiles/r02h_fused_crossover.jsonl): a wave of the fused kernel takes
+// T x (0.54 + 0.027 sum_c K_c + 0.16 D) microseconds, the pipeline 270 microseconds of launch latency plus 0.25 ns per
+// point.  Measured gains where it is chosen: 1.3 - 1.5x at the config-3 shape up to 1000 sequences, 1.2 - 1.8x at the
+// toy-robot shape up to 4000; the README set (5 + 5 variables, 1000 sequences) is a tie and stays on the pipeline.
 bool fused_estep_wanted(const dnbc_ctx *c, int64_t n_seq) {
   if (c->opt_fused_estep == 2) return false;
   const FusedPlan p = fused_plan(c);
@@ -701,8 +703,13 @@ bool fused_estep_wanted(const dnbc_ctx *c, int64_t n_seq) {
   int per_sm = (int)((size_t)(227 * 1024) / (p.smem + 1024));
   if (per_sm > 16) per_sm = 16;
   if (per_sm < 1) per_sm = 1;
-  const int64_t nbatch = (n_seq + p.a.PG - 1) / p.a.PG;
-  return 2 * nbatch <= (int64_t)3 * c->sm_count * per_sm;
+  const int64_t nbatch = (n_seq + p.a.PG - 1) / p.a.PG, capacity = (int64_t)c->sm_count * per_sm;
+  const double waves = (double)((nbatch + capacity - 1) / capacity);
+  int sumK = 0;
+  for (int v = 0; v < c->dm.C; ++v) sumK += c->K[v];
+  const double t_fused = waves * (double)c->Tmax * (0.54 + 0.027 * sumK + 0.16 * c->dm.D);
+  const double t_pipeline = 270.0 + 0.25e-3 * (double)n_seq * (double)c->Tmax;
+  return t_fused < t_pipeline;
 }
 
 // E-step of sequences [s0, s1) (points from p0) into the statistics buffer: one launch

@@ -19,6 +19,13 @@
 //     instead of ~6 for compare-and-select on every candidate;
 //   * the arg-max inside the winning block of 4 (and the runner-up inside it, for the tie flag) is
 //     recovered afterwards by re-forming just those 4 candidates (bit-identical adds);
+//   * exact pruning of source blocks (round 2): ncu shows the kernel bound by the ALU pipe (max / compare / select:
+//     76 % busy, FMA pipe 15 %), so the only way down is fewer candidates.  With LB = max_i (delta(i) + min_j ln a_ij),
+//     every destination's best candidate is >= LB; a source with delta(i) + max_j ln a_ij < LB - margin can neither
+//     win any destination nor come within the tie tolerance of a winner.  Each step starts by turning that test into
+//     one bit per block of 4 sources and sequence; the hot loop skips dead blocks (the test is warp-uniform: a warp's
+//     threads share their 4 sequences).  Paths, scores and tie flags are unchanged (same CRC over 2.5e7 points); on
+//     the reference generator's data at N = 512 about 10 % of the sources are live, i.e. a third of the blocks;
 //   * the back-trace is k_backtrace (k_decode.cu): one thread per sequence.
 #include "dnbc_internal.cuh"
 #include "packed_f32.cuh"
@@ -47,6 +54,8 @@ struct VtArgs {
   const float *E;        // [np][N]
   const float *logpi;    // [N]
   const float *LA;       // [NP][NP] padded ln A, -inf outside the active N x N block
+  const float *rowmax;   // [NP] max_j ln a_ij over the active destinations (-inf for an inactive source)
+  const float *rowmin;   // [NP] min_j ln a_ij over the active destinations (-inf as soon as one transition is impossible)
   const uint8_t *active;
   uint16_t *path;
   double *score;
@@ -63,6 +72,33 @@ __global__ void k_pad_logA(const float *__restrict__ logA, int lda, const uint8_
   }
 }
 
+// row extrema of the padded matrix over the active destinations (one warp per source row)
+__global__ void k_row_extrema(const float *__restrict__ LA, const uint8_t *__restrict__ active, int N, int NP,
+                              float *__restrict__ rowmax, float *__restrict__ rowmin) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= NP) return;
+  float mx = -INFINITY, mn = INFINITY;
+  if (warp < N && active[warp])
+    for (int j = lane; j < N; j += 32)
+      if (active[j]) {
+        const float v = LA[(int64_t)warp * NP + j];
+        mx = fmaxf(mx, v);
+        mn = fminf(mn, v);
+      }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if (lane == 0) {
+    rowmax[warp] = mx;
+    rowmin[warp] = mn == INFINITY ? -INFINITY : mn;
+  }
+}
+
+// candidates more than this below a destination's lower bound are pruned (four times the tie tolerance)
+#define DNBC_PRUNE_MARGIN (4.f * DNBC_TIE_TOL_F32)
+
 __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int N = a.N, NP = a.NP;
@@ -73,6 +109,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
   int64_t *sgb = sb + VT_BS;                                 // [VT_BS] global first point
   int *sT = (int *)(sgb + VT_BS);                            // [VT_BS]
   int *sflag = sT + VT_BS;                                   // [VT_BS] tie seen in this step
+  uint8_t *slive = (uint8_t *)(sflag + VT_BS);               // [VT_BS][NP / 32] one bit per block of 4 sources: may still win
+  const int nlw = NP / 32;
   __shared__ int sTmax, sna;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int bq0 = (w >> 1) * 4;                              // this thread's 4 sequences
@@ -101,6 +139,29 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
+  // live-block bits of this warp's two sequences from the delta rows in `rows` (any common shift of a row is fine)
+  auto make_masks = [&](const float *rows) {
+    for (int b = w * 2; b < w * 2 + 2; ++b) {
+      const float *d = rows + b * NP;
+      float lb = -INFINITY;
+      for (int j = lane; j < NP; j += 32) lb = fmaxf(lb, d[j] + __ldg(a.rowmin + j));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+      // (lb = -inf -- an impossible transition in every row that carries mass -- keeps every source that has mass)
+      const float thr = lb - DNBC_PRUNE_MARGIN;
+      for (int j0 = 0; j0 < NP; j0 += 32) {
+        const float v = d[j0 + lane] + __ldg(a.rowmax + j0 + lane);
+        const unsigned bal = __ballot_sync(0xffffffffu, v >= thr && v > -INFINITY);
+        if (lane == 0) {
+          unsigned bits = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bits |= ((bal >> (4 * q)) & 0xfu) ? (1u << q) : 0u;
+          slive[b * nlw + (j0 >> 5)] = (uint8_t)bits;
+        }
+      }
+    }
+  };
+
   for (int64_t s0 = a.s0 + (int64_t)blockIdx.x * VT_BS; s0 < a.s1; s0 += (int64_t)gridDim.x * VT_BS) {
     __syncthreads();
     if (tid == 0) sTmax = 0;
@@ -125,6 +186,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
     }
     if (Tmax > 1) load_tile(0, 0);
     __syncthreads();
+    make_masks(dbuf);
+    __syncthreads();
 
     for (int t = 1; t < Tmax; ++t) {
       const float *src = dbuf + ((t - 1) & 1) * VT_BS * NP;
@@ -146,8 +209,14 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
           if (g + 1 < G || t + 1 < Tmax) load_tile((g + 1) % G, (g + 1) & 1);
           const float *L = Lt + (g & 1) * (VT_IT * VT_JC) + jl;
           const float *d0 = src + bq0 * NP + it * VT_IT;
+          // live bits of this tile's 8 blocks for the thread's four sequences (warp-uniform)
+          unsigned lv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) lv[q] = slive[(bq0 + q) * nlw + it];
+          const unsigned lany = lv[0] | lv[1] | lv[2] | lv[3];
 #pragma unroll 2
           for (int ib = 0; ib < VT_IT / 4; ++ib) {
+            if (!((lany >> ib) & 1u)) continue;                // no sequence of this warp can use these 4 sources
             float4 Lr[4], dl[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) Lr[k] = *(const float4 *)(L + (ib * 4 + k) * VT_JC);
@@ -156,6 +225,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
             const int blk = it * (VT_IT / 4) + ib;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+              if (!((lv[q] >> ib) & 1u)) continue;
               float c[4][4];                                 // [source k][destination x]
               add2s(Lr[0].x, Lr[0].y, dl[q].x, c[0][0], c[0][1]);
               add2s(Lr[0].z, Lr[0].w, dl[q].x, c[0][2], c[0][3]);
@@ -243,6 +313,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
           if (live && sflag[b] && a.tie) a.tie[sgb[b] + t] |= 2;
         }
       }
+      make_masks(dst);                                       // (each lane re-reads only what it wrote above)
       __syncthreads();
     }
     // ---- last state: first maximum over the active states, tie flag, score
@@ -289,20 +360,27 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_viterbi_tile(VtArgs a) {
 
 }  // namespace
 
+static size_t vt_smem(int NP) {
+  return (size_t)(2 * VT_BS * NP + 2 * VT_IT * VT_JC) * sizeof(float) + VT_BS * (8 + 8 + 8 + 4 + 4) + VT_BS * (NP / 32) + 64;
+}
+// (the two delta buffers of 32 sequences are 8 NP x 32 bytes: padded state counts above 512 do not fit one SM's shared
+// memory and stay on k_decode_block; a third stage of the ln A ring was measured slower, 647 vs 608 ms)
 bool viterbi_tile_supported(const dnbc_ctx *c) {
-  return c->dm.Npad >= VT_JC && c->dm.Npad % VT_JC == 0 && c->dm.Npad <= 1024;
+  return c->dm.Npad >= VT_JC && c->dm.Npad % VT_JC == 0 && vt_smem(c->dm.Npad) <= 227 * 1024;
 }
 
 int launch_viterbi_tile(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path, double *score,
                         uint8_t *tie, uint16_t *bp) {
   const int N = c->dm.N, NP = c->dm.Npad;
-  if (!c->vt_logA) {
-    if (cudaMalloc((void **)&c->vt_logA, (size_t)NP * NP * sizeof(float)) != cudaSuccess) return DNBC_ENOMEM;
+  if (!c->vt_logA) {                                         // [NP][NP] padded ln A, then its row maxima and minima
+    if (cudaMalloc((void **)&c->vt_logA, ((size_t)NP * NP + 2 * NP) * sizeof(float)) != cudaSuccess) return DNBC_ENOMEM;
   }
-  c->launches++;
+  float *rowmax = c->vt_logA + (size_t)NP * NP, *rowmin = rowmax + NP;
+  c->launches += 2;
   k_pad_logA<<<c->sm_count * 2, 256, 0, c->stream>>>(c->t_logA, NP, c->d_active, N, NP, c->vt_logA);
-  VtArgs a{N, NP, c->d_off, s0, s1, p0, E, c->t_logpi, c->vt_logA, c->d_active, path, score, tie, bp};
-  const size_t smem = (size_t)(2 * VT_BS * NP + 2 * VT_IT * VT_JC) * sizeof(float) + VT_BS * (8 + 8 + 8 + 4 + 4) + 64;
+  k_row_extrema<<<(NP * 32 + 255) / 256, 256, 0, c->stream>>>(c->vt_logA, c->d_active, N, NP, rowmax, rowmin);
+  VtArgs a{N, NP, c->d_off, s0, s1, p0, E, c->t_logpi, c->vt_logA, rowmax, rowmin, c->d_active, path, score, tie, bp};
+  const size_t smem = vt_smem(NP);
   const int64_t batches = (s1 - s0 + VT_BS - 1) / VT_BS;
   const int grid = (int)(batches < c->sm_count ? batches : c->sm_count);
   cudaFuncSetAttribute(k_viterbi_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -203,9 +203,9 @@ enum {
   /* 1 = keep the register-resident recursions (N <= 64) on their large-input variant -- four
    * sequences per lane group, exact lane groups -- for inputs that fit one wave (tests). */
   DNBC_OPT_FB2_INTERLEAVE = 2,
-  /* E-step path for N <= 16: 0 = automatic (the single-launch kernel of k_fused.cu when the resident
-   * sequences fit about one and a half waves of it -- it is latency-optimal, not throughput-optimal), 1 = always the
-   * fused kernel when the shape fits its shared memory, 2 = always the general pipeline. */
+  /* E-step path for N <= 16: 0 = automatic (the single-launch kernel of k_fused.cu while its estimated time
+   * is below the general pipeline's launch-latency floor -- it is latency-optimal, not throughput-optimal), 1 = always
+   * the fused kernel when the shape fits its shared memory, 2 = always the general pipeline. */
   DNBC_OPT_FUSED_ESTEP = 3
 };
 int dnbc_set_option(dnbc_ctx *ctx, int option, int64_t value);

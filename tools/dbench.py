@@ -9,11 +9,6 @@ truth = workloads.true_params(wl)
 ctx = nat.Context(wl.N, [wl.V] * wl.D, [wl.K] * wl.C, device=0)
 ctx.set_params(truth["pi"], truth["A"], truth["B"], truth["w"], truth["mu"], truth["var"])
 ctx.generate(seqs, wl.T, 4321)
-out = {}
-for name, env in (("new", None), ("old", "1")):
-    if env: os.environ["DNBC_NO_VITERBI2"] = env
-    # (the switch is read once per process: run the old path in a child)
-    break
 path, score, tie = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32, want_tie=True)
 ctx.profile_enable(True)
 t0 = time.perf_counter()
