@@ -62,28 +62,40 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int KP>
+// ODD: the mixtures have 2 KP + 1 components and the last one travels alone in scalar registers (K = 3, 5, 7 with the
+// same K for every variable): a padded pair would cost an exponential and seven packed instructions per point for nothing.
+template <int KP, bool ODD>
 struct Coef {
   u64 s2[KP], m2[KP], cc2[KP];   // z = x s + m ; exponent = cc - z^2 (log2 units), two components per register pair
+  float s1, m1, c1;
 };
-template <int KP>
+template <int KP, bool ODD>
 struct Acc {
   u64 S0[KP], S1[KP], S2[KP];    // sum r, sum r z, sum r z^2 over the current window
+  float t0, t1, t2;
 };
 #ifndef S2_TTRICK
 #define S2_TTRICK 1
 #endif
-template <int KP>
+template <int KP, bool ODD>
 struct Pend {
   u64 z[KP], e[KP];
 #if S2_TTRICK
   u64 a[KP];                     // exponent arguments c' - z^2 (see stage2)
 #endif
+  float z1, e1, a1;
 };
 
 // stage 1 of a point: standardised coordinate and the 2 KP exponentials
-template <int KP>
-__device__ __forceinline__ void stage1(const Coef<KP> &q, u64 xx, Pend<KP> &n) {
+template <int KP, bool ODD>
+__device__ __forceinline__ void stage1(const Coef<KP, ODD> &q, u64 xx, Pend<KP, ODD> &n) {
+  if (ODD) {
+    float x, xhi;
+    unpk(xx, x, xhi);
+    n.z1 = fmaf(x, q.s1, q.m1);
+    n.a1 = fmaf(-n.z1, n.z1, q.c1);
+    n.e1 = ex2_approx(n.a1);
+  }
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     n.z[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
@@ -96,12 +108,12 @@ __device__ __forceinline__ void stage1(const Coef<KP> &q, u64 xx, Pend<KP> &n) {
   }
 }
 // mixture sum of a pending point (the underflow decision is taken on exactly this value, here and in the redo)
-template <int KP>
-__device__ __forceinline__ float mix_sum(const Pend<KP> &p) {
+template <int KP, bool ODD>
+__device__ __forceinline__ float mix_sum(const Pend<KP, ODD> &p) {
   u64 sum2 = p.e[0];
 #pragma unroll
   for (int kp = 1; kp < KP; ++kp) sum2 = add2(sum2, p.e[kp]);
-  return hsum(sum2);
+  return ODD ? hsum(sum2) + p.e1 : hsum(sum2);
 }
 // stage 2: normalise by the mixture sum, weight by the posterior, accumulate the three moments.
 // No predicates: the sum is clamped to the smallest normal float, so the weight g / sum is finite and a mixture
@@ -110,9 +122,9 @@ __device__ __forceinline__ float mix_sum(const Pend<KP> &p) {
 // at a point ~9 sigma away from all of its components, where fp32 has flushed part of the mixture) sends the
 // block through the exponent-shifted re-evaluation.
 constexpr float HBIG = 1e18f;
-template <int KP>
-__device__ __forceinline__ float stage2(Acc<KP> &a, const Pend<KP> &p, float g) {
-  const float sum = mix_sum<KP>(p);
+template <int KP, bool ODD>
+__device__ __forceinline__ float stage2(Acc<KP, ODD> &a, const Pend<KP, ODD> &p, float g) {
+  const float sum = mix_sum<KP, ODD>(p);
   const float inv = g * rcp_approx(fmaxf(sum, 1.17549435e-38f));
   const u64 inv2 = pk(inv, inv);
 #pragma unroll
@@ -130,14 +142,30 @@ __device__ __forceinline__ float stage2(Acc<KP> &a, const Pend<KP> &p, float g) 
     a.S2[kp] = fma2(rz, p.z[kp], a.S2[kp]);
 #endif
   }
+  if (ODD) {
+    const float r = p.e1 * inv;
+    a.t0 += r;
+    a.t1 = fmaf(r, p.z1, a.t1);
+#if S2_TTRICK
+    a.t2 = fmaf(r, p.a1, a.t2);
+#else
+    a.t2 = fmaf(r * p.z1, p.z1, a.t2);
+#endif
+  }
   return inv;
 }
 // exponent-shifted evaluation for a point whose mixture sum underflows fp32 (rare; same as stat_point of k_mixture.cu)
-template <int KP>
-__device__ __forceinline__ void shifted_point(const Coef<KP> &q, Acc<KP> &a, float x, float g) {
+template <int KP, bool ODD>
+__device__ __forceinline__ void shifted_point(const Coef<KP, ODD> &q, Acc<KP, ODD> &a, float x, float g) {
   const u64 xx = pk(x, x);
   u64 a2[KP], z2[KP];
   float mx = -INFINITY;
+  float z1 = 0.f, a1 = -INFINITY;
+  if (ODD) {
+    z1 = fmaf(x, q.s1, q.m1);
+    a1 = fmaf(-z1, z1, q.c1);
+    mx = a1;
+  }
 #pragma unroll
   for (int kp = 0; kp < KP; ++kp) {
     z2[kp] = fma2(xx, q.s2[kp], q.m2[kp]);
@@ -154,7 +182,8 @@ __device__ __forceinline__ void shifted_point(const Coef<KP> &q, Acc<KP> &a, flo
     e2[kp] = ex2_2(add2(a2[kp], nm));
     sum2 = add2(sum2, e2[kp]);
   }
-  const float sum = hsum(sum2);
+  const float e1 = ODD ? ex2_approx(a1 - mx) : 0.f;
+  const float sum = hsum(sum2) + e1;
   const float inv = sum > 0.f ? g * rcp_approx(sum) : 0.f;
   const u64 inv2 = pk(inv, inv);
 #pragma unroll
@@ -170,6 +199,16 @@ __device__ __forceinline__ void shifted_point(const Coef<KP> &q, Acc<KP> &a, flo
     a.S2[kp] = fma2(rz, z2[kp], a.S2[kp]);
 #endif
   }
+  if (ODD) {
+    const float r = e1 * inv;
+    a.t0 += r;
+    a.t1 = fmaf(r, z1, a.t1);
+#if S2_TTRICK
+    a.t2 = fmaf(r, a1, a.t2);
+#else
+    a.t2 = fmaf(r * z1, z1, a.t2);
+#endif
+  }
 }
 
 // shared memory of one warp: posterior tiles (2 stages), observation records (2 stages, 33 entries: the pipeline
@@ -182,15 +221,15 @@ struct alignas(16) Rec { float x0, x1; int voff; int pad; };
 // pipeline buffers alternate, so nothing is copied between points.  Returns the largest weight g / sum seen.
 // GRP (state counts up to 32): a warp step covers PG points x LG lanes, so a block is 32 steps = 32 PG points; gstep /
 // rstep are the distances between consecutive steps in the posterior tile (floats) and the record array.
-template <int KP, bool HAS_C, bool HAS_D, bool GRP>
-__device__ __forceinline__ float block32(const Coef<KP> &q, Acc<KP> &acc, const float *gt, const Rec *rec, char *bdb, float &gsl,
+template <int KP, bool ODD, bool HAS_C, bool HAS_D, bool GRP>
+__device__ __forceinline__ float block32(const Coef<KP, ODD> &q, Acc<KP, ODD> &acc, const float *gt, const Rec *rec, char *bdb, float &gsl,
                                          bool gsum_on, int gstep_, int rstep_) {
   const int gstep = GRP ? gstep_ : 32, rstep = GRP ? rstep_ : 1;
   float hmax = 0.f;
-  Pend<KP> pa, pb;
+  Pend<KP, ODD> pa, pb;
   if (HAS_C) {
     const float4 r0 = *reinterpret_cast<const float4 *>(rec);
-    stage1<KP>(q, pk(r0.x, r0.y), pa);
+    stage1<KP, ODD>(q, pk(r0.x, r0.y), pa);
   }
   const float4 *rp = reinterpret_cast<const float4 *>(rec);
 #pragma unroll 1
@@ -200,11 +239,11 @@ __device__ __forceinline__ float block32(const Coef<KP> &q, Acc<KP> &acc, const 
       const float g0 = gt[gstep * h], g1 = gt[gstep * h + gstep];
       if (HAS_C) {
         const float2 x1 = *reinterpret_cast<const float2 *>(rp + (h + 1) * rstep);
-        stage1<KP>(q, pk(x1.x, x1.y), pb);
-        hmax = fmaxf(hmax, stage2<KP>(acc, pa, g0));
+        stage1<KP, ODD>(q, pk(x1.x, x1.y), pb);
+        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, pa, g0));
         const float2 x2 = *reinterpret_cast<const float2 *>(rp + (h + 2) * rstep);
-        stage1<KP>(q, pk(x2.x, x2.y), pa);
-        hmax = fmaxf(hmax, stage2<KP>(acc, pb, g1));
+        stage1<KP, ODD>(q, pk(x2.x, x2.y), pa);
+        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, pb, g1));
       }
       if (HAS_D) {
         // categorical histogram: bins[symbol][state] += gamma
@@ -227,7 +266,7 @@ constexpr int PGMAX = 4;         // points per warp step in the grouped layout (
 //              the [32 points][32 states] slice of GA.
 // GRP = true : N <= 32; lane = (point slot gi, state lj), a block is 32 steps of PG points, the tile is the contiguous
 //              [32 PG points][N] piece of GA.  Lanes past the last whole group and padded states carry zero weight.
-template <int KP, bool GRP>
+template <int KP, bool ODD, bool GRP>
 __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
@@ -259,8 +298,8 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   float *zero_word = bins + bin_floats;
   if (GRP && lane == 0) *zero_word = 0.f;
 
-  Coef<KP> q;
-  Acc<KP> acc;
+  Coef<KP, ODD> q;
+  Acc<KP, ODD> acc;
 #if S2_TTRICK
   // Responsibilities do not change when every component of a mixture is scaled by the same factor, so the log2
   // constants are shifted per (variable, state) to put the largest at CREF = E[z^2] of a well-fitted component:
@@ -294,6 +333,19 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
     }
     q.s2[kp] = pk(v[0], v[1]); q.m2[kp] = pk(v[2], v[3]); q.cc2[kp] = pk(v[4], v[5]);
     acc.S0[kp] = acc.S1[kp] = acc.S2[kp] = 0ull;
+  }
+  q.s1 = q.m1 = 0.f;
+  q.c1 = -20000.f;
+  acc.t0 = acc.t1 = acc.t2 = 0.f;
+  if (ODD && has_c && lane_on) {                            // the odd last component (every variable has 2 KP + 1)
+    const int64_t o = ((int64_t)u * Kmax + 2 * KP) * Npad + j;
+    q.s1 = a.tb.gs[o];
+    q.m1 = a.tb.gm[o];
+#if S2_TTRICK
+    q.c1 = fmaxf(a.tb.gc[o] + kappa, -20000.f);
+#else
+    q.c1 = a.tb.gc[o];
+#endif
   }
   // contiguous run of whole blocks per CTA column
   const int per = (a.nblk + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -366,9 +418,9 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
     const int gstep = GRP ? (lane_on ? PG * N : 0) : 32;
     const Rec *rec0 = rec + (GRP ? (gi < PG ? gi : 0) : 0);
     float gsl = 0.f, hmax;
-    if (has_c && has_d) hmax = block32<KP, true, true, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
-    else if (has_c) hmax = block32<KP, true, false, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
-    else hmax = block32<KP, false, true, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
+    if (has_c && has_d) hmax = block32<KP, ODD, true, true, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
+    else if (has_c) hmax = block32<KP, ODD, true, false, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
+    else hmax = block32<KP, ODD, false, true, GRP>(q, acc, gt, rec0, bdb, gsl, gsum_on, gstep, PG);
     gs += (double)gsl;
     if (has_c && __any_sync(0xffffffffu, hmax > HBIG)) {
       // rare: a state with posterior mass at a point where fp32 has flushed (part of) its mixture.  Each lane takes
@@ -377,12 +429,12 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
 #pragma unroll 1
       for (int p = 0; p < 32; ++p) {
         const float x = rec0[p * PG].x0, g = gt[p * gstep];
-        Pend<KP> pr;
-        stage1<KP>(q, pk(x, x), pr);
-        const float inv = g * rcp_approx(fmaxf(mix_sum<KP>(pr), 1.17549435e-38f));
+        Pend<KP, ODD> pr;
+        stage1<KP, ODD>(q, pk(x, x), pr);
+        const float inv = g * rcp_approx(fmaxf(mix_sum<KP, ODD>(pr), 1.17549435e-38f));
         const bool redo = inv > HBIG;
-        stage2<KP>(acc, pr, redo ? -g : 0.f);
-        shifted_point<KP>(q, acc, x, redo ? g : 0.f);
+        stage2<KP, ODD>(acc, pr, redo ? -g : 0.f);
+        shifted_point<KP, ODD>(q, acc, x, redo ? g : 0.f);
       }
     }
     inwin += TPB;
@@ -420,7 +472,28 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
             }
           }
         }
+        if (ODD && acc.t0 != 0.f) {
+          const int k = 2 * KP;
+          const int64_t dst = ((int64_t)u * N + j) * Kmax + k;
+          const double s = (double)q.s1;
+          double m0 = (double)acc.t0, m1 = 0.0, m2d = 0.0;
+          if (s > 0.0) {
+            const double delta = -(double)q.m1 / s - a.mu_old[dst];
+#if S2_TTRICK
+            const double zz = (double)q.c1 * (double)acc.t0 - (double)acc.t2;
+#else
+            const double zz = (double)acc.t2;
+#endif
+            const double c1 = (double)acc.t1 / s, c2 = zz / (s * s);
+            m1 = c1 + delta * m0;
+            m2d = c2 + 2.0 * delta * c1 + delta * delta * m0;
+          }
+          atomicAdd(a.gmm + 3 * dst + 0, m0);
+          atomicAdd(a.gmm + 3 * dst + 1, m1);
+          atomicAdd(a.gmm + 3 * dst + 2, m2d);
+        }
       }
+      acc.t0 = acc.t1 = acc.t2 = 0.f;
 #pragma unroll
       for (int kp = 0; kp < KP; ++kp) acc.S0[kp] = acc.S1[kp] = acc.S2[kp] = 0ull;
       if (gsum_on) {
@@ -489,18 +562,25 @@ int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
   if (gx > maxgx) gx = maxgx;
   if (gx < 1) gx = 1;
   const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
-  const int KP = (d.Kmax + 1) / 2;
+  // every variable with the same odd K >= 3: the last component in scalar registers instead of a padded pair
+  bool odd = d.C > 0 && (d.Kmax & 1) && d.Kmax >= 3;
+  for (int v = 0; v < d.C; ++v) odd = odd && c->K[v] == d.Kmax;
+  const int KP = odd ? d.Kmax / 2 : (d.Kmax + 1) / 2;
+#define STATS2_LAUNCH(KP_, ODD_, GRP_)                                                                            \
+  do {                                                                                                            \
+    cudaFuncSetAttribute(k_stats2<KP_, ODD_, GRP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    k_stats2<KP_, ODD_, GRP_><<<grid, nw * 32, smem, c->stream>>>(a);                                              \
+  } while (0)
 #define STATS2_CASE(KP_)                                                                                          \
   if (KP == KP_) {                                                                                                \
-    if (grp) {                                                                                                    \
-      cudaFuncSetAttribute(k_stats2<KP_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-      k_stats2<KP_, true><<<grid, nw * 32, smem, c->stream>>>(a);                                                  \
+    if (odd && KP_ < 4) {                                                                                         \
+      if (grp) STATS2_LAUNCH(KP_, true, true); else STATS2_LAUNCH(KP_, true, false);                              \
     } else {                                                                                                      \
-      cudaFuncSetAttribute(k_stats2<KP_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-      k_stats2<KP_, false><<<grid, nw * 32, smem, c->stream>>>(a);                                                 \
+      if (grp) STATS2_LAUNCH(KP_, false, true); else STATS2_LAUNCH(KP_, false, false);                            \
     }                                                                                                             \
   }
   STATS2_CASE(1) STATS2_CASE(2) STATS2_CASE(3) STATS2_CASE(4)
 #undef STATS2_CASE
+#undef STATS2_LAUNCH
   return nblk * TPB;
 }

@@ -433,3 +433,26 @@ def test_fused_estep_outliers_and_long_sequences(oracle):
         assert ctx.launch_count() - l0 >= 4
         g2 = oracle.split_stats(m2, ctx.em_get_stats())
     assert abs(g2["ll"] - w2["ll"]) <= TOL * abs(w2["ll"])
+
+
+def test_state_counts_above_512(oracle):
+    """N = 600 pads to 1024: beyond the tcgen05 recursion (256 / 512) and beyond the max-plus Viterbi tiles (two
+    delta buffers of 32 sequences no longer fit one SM's shared memory), so the CTA-per-sequence kernels run."""
+    m = random_model(oracle, 600, [4], [2], 491, transitions_per_state=12)
+    data = sample(oracle, m, [25, 9, 1, 30], 492)
+    q = perturb(oracle, m, 493)
+    want = oracle.split_stats(q, oracle.estep(q, data))
+    opath, oscore, otie = oracle.decode(q, data, oracle.DECODE_BACKTRACE)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False)
+        ctx.em_estep()
+        got = oracle.split_stats(q, ctx.em_get_stats())
+        p32, s32, t32 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+        p64, s64, t64 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F64)
+    assert abs(got["ll"] - want["ll"]) <= TOL * abs(want["ll"])
+    np.testing.assert_allclose(got["gamma"], want["gamma"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(got["xi"], want["xi"], rtol=1e-4, atol=1e-4)
+    _paths_equal_except_ties(p32, opath, t32, otie, data.off, True)
+    _paths_equal_except_ties(p64, opath, t64, otie, data.off, True)
+    np.testing.assert_allclose(s32, oscore, rtol=1e-5)
+    np.testing.assert_allclose(s64, oscore, rtol=1e-11)
