@@ -242,7 +242,15 @@ __global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_
 #pragma unroll
       for (int r = 0; r < R; ++r) bcur[q][r] = ex2_approx((bcur[q][r] - mcur[q]) * (float)DNBC_LOG2E);
     }
-    for (int t = 0; t < Tmax; ++t) {
+    // The ring of requested rows is indexed statically: the step loop is unrolled PF times and step t consumes
+    // and refills slot t % PF.  A ring that moves up by register copies touches every requested row one step after
+    // its load was issued, and the copy waits for it (ncu, profiles/r02t_ncu_n10_summary.txt: 44 % of the forward
+    // kernel's stall samples on the first copy at the loop top): the rows were in effect requested one step ahead.
+    for (int t0 = 0; t0 < Tmax; t0 += PF) {
+#pragma unroll
+     for (int u = 0; u < PF; ++u) {
+      const int t = t0 + u;
+      if (t >= Tmax) break;
       // phases run over all SQ sequences so their dependency chains interleave; only the two
       // __syncwarp()s around the shared-memory exchange order the instruction stream
       float acc[SQ][R], csum[SQ], mnext[SQ];
@@ -264,12 +272,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         csum[q] = 0.f;
-        mnext[q] = ering[0][q][0];
+        mnext[q] = ering[u][q][0];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           acc[q][r] *= bcur[q][r];
           csum[q] += acc[q][r];
-          mnext[q] = fmaxf(mnext[q], ering[0][q][r]);
+          mnext[q] = fmaxf(mnext[q], ering[u][q][r]);
         }
       }
       GroupRed<LG>::template sum_max<SQ>(csum, mnext, mask, lj, base);
@@ -286,16 +294,15 @@ __global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_
           a.cs[pt[q] + t] = csum[q];
           ll += (double)(lg2_approx(csum[q]) * (float)DNBC_LN2) + (double)mcur[q];
         }
-        // next step's emission factor; the ring moves up and its tail is requested
+        // next step's emission factor; its ring slot is refilled with the row PF steps further on
         mcur[q] = mnext[q] == -INFINITY ? 0.f : mnext[q];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          bcur[q][r] = ex2_approx((ering[0][q][r] - mcur[q]) * (float)DNBC_LOG2E);
-#pragma unroll
-          for (int i = 0; i + 1 < PF; ++i) ering[i][q][r] = ering[i + 1][q][r];
-          ering[PF - 1][q][r] = load_e(q, r, t + 1 + PF);
+          bcur[q][r] = ex2_approx((ering[u][q][r] - mcur[q]) * (float)DNBC_LOG2E);
+          ering[u][q][r] = load_e(q, r, t + 1 + PF);
         }
       }
+     }
     }
   }
   if (lj == 0 && ll != 0.0) atomicAdd(a.stats, ll);
@@ -309,7 +316,9 @@ template <int LG, int R, int SQ, bool XI>
 __global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_backward2(Fb2Args a) {
   static_assert(!XI || R == 1, "fused transition statistics need the whole row in one register line");
   constexpr int NP = fb2_np(LG, R), PG = 32 / LG;
-  constexpr int PF = R == 1 ? 3 : 1;                        // rows in flight ahead of the step
+  // (three rings of rows here: two slots each measure faster than three -- 1.21 vs 1.28 ms per 2e7 points at N = 10 --
+  // and four spill: 1.59 ms; the forward sweep has one ring and wants three, 0.80 vs 0.83 ms)
+  constexpr int PF = R == 1 ? 2 : 1;                        // rows in flight ahead of the step
   __shared__ __align__(16) float sv[FB_WARPS][PG][SQ][NP < 4 ? 4 : NP];
   const int N = a.dm.N, Npad = a.dm.Npad;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, gi = lane / LG;
@@ -399,12 +408,17 @@ __global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_
       }
     }
     // sequences of a pair are aligned at their LAST step: step index k counts back from it
-    for (int k = 0; k < Tmax; ++k) {
+    // (ring slots are indexed statically, k % PF, as in the forward sweep)
+    for (int k0 = 0; k0 < Tmax; k0 += PF) {
+#pragma unroll
+     for (int u = 0; u < PF; ++u) {
+      const int k = k0 + u;
+      if (k >= Tmax) break;
       float al[SQ][R], mnext[SQ];
 #pragma unroll
       for (int q = 0; q < SQ; ++q)
 #pragma unroll
-        for (int r = 0; r < R; ++r) al[q][r] = alr[0][q][r];
+        for (int r = 0; r < R; ++r) al[q][r] = alr[u][q][r];
       if (k > 0) {
 #pragma unroll
         for (int q = 0; q < SQ; ++q) {
@@ -438,11 +452,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_
 #pragma unroll
       for (int q = 0; q < SQ; ++q) {
         gsumq[q] = 0.f;
-        mnext[q] = ering[0][q][0];
+        mnext[q] = ering[u][q][0];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           gsumq[q] = fmaf(al[q][r], beta[q][r], gsumq[q]);
-          mnext[q] = fmaxf(mnext[q], ering[0][q][r]);
+          mnext[q] = fmaxf(mnext[q], ering[u][q][r]);
         }
       }
       GroupRed<LG>::template sum_max<SQ>(gsumq, mnext, mask, lj, base);
@@ -457,24 +471,18 @@ __global__ void __launch_bounds__(FB_WARPS * 32, (R == 1 && LG < 32) ? 4 : 0) k_
           if (t >= 0 && ir[r] < N) a.GA[row[q] + (int64_t)t * N + ir[r]] = g;
           if (t == 0) piacc[r] += (double)g;
         }
-        // next iteration's factor (E_t, c_t are its "t+1" quantities); the rings move up, tails are requested
+        // next iteration's factor (E_t, c_t are its "t+1" quantities); the ring slots are refilled PF steps ahead
         const float mn = mnext[q] == -INFINITY ? 0.f : mnext[q];
-        const float ic = rcp_approx(cring[0][q]);
-#pragma unroll
-        for (int i = 0; i + 1 < PF; ++i) cring[i][q] = cring[i + 1][q];
-        cring[PF - 1][q] = load_c(q, t - PF);
+        const float ic = rcp_approx(cring[u][q]);
+        cring[u][q] = load_c(q, t - PF);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          bu[q][r] = ex2_approx((ering[0][q][r] - mn) * (float)DNBC_LOG2E) * ic;
-#pragma unroll
-          for (int i = 0; i + 1 < PF; ++i) {
-            ering[i][q][r] = ering[i + 1][q][r];
-            alr[i][q][r] = alr[i + 1][q][r];
-          }
-          ering[PF - 1][q][r] = load_e(q, r, t - PF);
-          alr[PF - 1][q][r] = load_al(q, r, t - PF);
+          bu[q][r] = ex2_approx((ering[u][q][r] - mn) * (float)DNBC_LOG2E) * ic;
+          ering[u][q][r] = load_e(q, r, t - PF);
+          alr[u][q][r] = load_al(q, r, t - PF);
         }
       }
+     }
     }
     xcount += Tmax * SQ;
     if (XI && xcount >= 4096) xi_flush();

@@ -311,6 +311,284 @@ __global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
 }
 
 // ---------------------------------------------------------------------------------
+// K1 emission, packed over POINTS (k_emission_px)
+// ---------------------------------------------------------------------------------
+// The same sums as k_emission_pk, but the two halves of a packed instruction are two consecutive points of ONE
+// mixture component instead of two components at one point.  A component's coefficients then enter the FFMA2 as
+// scalar broadcast operands (SASS: FFMA2 R, R.F32x2, R.F32, R.F32), so
+//   * an odd component count costs nothing (K = 3 is three component steps, not a pair plus a scalar tail with
+//     its own code path), and no per-variable count checks run inside the component loop;
+//   * the mixture sums of a lane's four points are two packed registers: no horizontal add, packed log2
+//     arguments, packed accumulation; one underflow test per variable covers the four points;
+//   * lane groups below 32 states (N = 10: three points x 10 lanes) read 4 consecutive points per lane with one
+//     16-byte load like the full-warp layout does.
+// ncu before (profiles/r02t_ncu_n512_summary.txt, N = 512, K = 3): 40 warp instructions per (point, variable,
+// 32 states), issue 77 %, MUFU 63 %; the component-packed kernel stays in use where every variable has the same
+// EVEN component count (the scale-out shape: MUFU 90 %).
+// KU > 0: every variable has exactly KU components (unrolled, log2 shared by pairs of variables);
+// KU = 0: per-variable counts (runtime loop, one log2 per variable).
+template <int KU>
+struct PxScale {
+  static constexpr float SHIFT = KU > 0 ? EMIT_SHIFT : 0.f;
+  static constexpr float TINY = KU > 0 ? 1e-18f : 1e-30f;
+};
+__device__ __forceinline__ u64 lg2_2(u64 a) {
+  u64 d;
+  asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tlg2.approx.ftz.f32 lo, lo;\n\tlg2.approx.ftz.f32 hi, hi;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}" : "=l"(d) : "l"(a));
+  return d;
+}
+// exponent-shifted evaluation of one (point, state, variable) whose mixture sum underflowed fp32: log2 of the sum
+// without the staged shift, finite wherever the reference's fp64 sum is finite (rare; kept out of line)
+__device__ __noinline__ float emit_px_slow(const float4 *ps, int kc, float x, float shift) {
+  float mx = -INFINITY;
+  for (int k = 0; k < kc; ++k) {
+    const float4 q = ps[k * 32];
+    const float z = fmaf(x, q.x, q.y);
+    mx = fmaxf(mx, fmaf(-z, z, q.z));
+  }
+  if (mx == -INFINITY) return -INFINITY;                     // no component has mass
+  float s = 0.f;
+  for (int k = 0; k < kc; ++k) {
+    const float4 q = ps[k * 32];
+    const float z = fmaf(x, q.x, q.y);
+    s += ex2_approx(fmaf(-z, z, q.z) - mx);
+  }
+  return mx + lg2_approx(s) - shift;
+}
+// one variable, 4 points (x01, x23): log2 mixture density added to acc01 / acc23.  PAIR as in emit_var.
+template <int KU, int PAIR>
+__device__ __forceinline__ void emit_var_px(const float4 *ps, int kc, u64 x01, u64 x23, u64 &acc01, u64 &acc23,
+                                            u64 &hold01, u64 &hold23) {
+  constexpr float SH = PxScale<KU>::SHIFT;
+  u64 s01 = 0ull, s23 = 0ull;
+  if (KU > 0) {
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+      const float4 q = ps[k * 32];
+      const u64 sb = pk(q.x, q.x), mb = pk(q.y, q.y), cb = pk(q.z, q.z);
+      const u64 z01 = fma2(x01, sb, mb), z23 = fma2(x23, sb, mb);
+      const u64 e01 = ex2_2(fnma2(z01, z01, cb)), e23 = ex2_2(fnma2(z23, z23, cb));
+      s01 = k == 0 ? e01 : add2(s01, e01);
+      s23 = k == 0 ? e23 : add2(s23, e23);
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < kc; ++k) {
+      const float4 q = ps[k * 32];
+      const u64 sb = pk(q.x, q.x), mb = pk(q.y, q.y), cb = pk(q.z, q.z);
+      const u64 z01 = fma2(x01, sb, mb), z23 = fma2(x23, sb, mb);
+      s01 = add2(s01, ex2_2(fnma2(z01, z01, cb)));
+      s23 = add2(s23, ex2_2(fnma2(z23, z23, cb)));
+    }
+  }
+  float v[4];
+  unpk(s01, v[0], v[1]);
+  unpk(s23, v[2], v[3]);
+  if (fminf(fminf(v[0], v[1]), fminf(v[2], v[3])) < PxScale<KU>::TINY) {
+    // some point's mixture underflowed (every component > ~13 sigma away) or has no mass: its term is completed
+    // here and it joins the log2 below as the neutral factor 2^SHIFT
+    float x[4], ac[4];
+    unpk(x01, x[0], x[1]);
+    unpk(x23, x[2], x[3]);
+    unpk(acc01, ac[0], ac[1]);
+    unpk(acc23, ac[2], ac[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (v[i] < PxScale<KU>::TINY) {
+        ac[i] += emit_px_slow(ps, KU > 0 ? KU : kc, x[i], SH);
+        v[i] = KU > 0 ? 1073741824.f : 1.f;
+      }
+    acc01 = pk(ac[0], ac[1]);
+    acc23 = pk(ac[2], ac[3]);
+    s01 = pk(v[0], v[1]);
+    s23 = pk(v[2], v[3]);
+  }
+  if (PAIR == 1) {
+    hold01 = s01;
+    hold23 = s23;
+  } else if (PAIR == 2) {
+    const u64 back = pk(-2.f * SH, -2.f * SH);
+    acc01 = add2(acc01, add2(lg2_2(mul2(hold01, s01)), back));
+    acc23 = add2(acc23, add2(lg2_2(mul2(hold23, s23)), back));
+  } else if (SH != 0.f) {
+    const u64 back = pk(-SH, -SH);
+    acc01 = add2(acc01, add2(lg2_2(s01), back));
+    acc23 = add2(acc23, add2(lg2_2(s23), back));
+  } else {
+    acc01 = add2(acc01, lg2_2(s01));
+    acc23 = add2(acc23, lg2_2(s23));
+  }
+}
+
+// Observations reach the arithmetic through shared memory: a warp's next group of points (4 consecutive points per
+// lane group, every variable) is requested with cp.async one whole group ahead and read back with one broadcast
+// LDS.128 (LDS.32 for the symbols) per variable.  Register prefetch of the next variable's observations does not
+// survive ptxas here: the loaded registers are copied at the merge of the aligned / ragged load paths, and the copy
+// waits for the load (ncu of the first version of this kernel: 35 % of the stall samples on those copies).
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_px() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_px() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int PX_WARPS = 16;
+// shared memory: coefficients of the 32-state slice [C][KS][32] x {s, m, c, -}, the categorical table
+// [D][Vmax+1][32], then per warp two stages of observations [C][PG] x float4 and symbols [D][PG] x uint32
+template <int KU>
+__global__ void __launch_bounds__(PX_WARPS * 32, 2) k_emission_px(EmitArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
+  const int KS = KU > 0 ? KU : Kmax;                        // component slots per variable
+  const int LG = a.LG, PG = 32 / LG;
+  float4 *sm_q = (float4 *)smraw;                           // [C*KS*32]
+  float *sm_cat = (float *)(sm_q + (size_t)C * KS * 32);    // [D*(Vmax+1)*32]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lj = lane % LG, lp = lane / LG;
+  const int xstage = C * PG, vstage = (D * PG + 3) & ~3;    // float4 / uint32 entries of one stage
+  float4 *xs = (float4 *)(sm_cat + (size_t)D * (Vmax + 1) * 32) + (size_t)w * 2 * xstage;          // [2][C][PG]
+  uint32_t *vs = (uint32_t *)((float4 *)(sm_cat + (size_t)D * (Vmax + 1) * 32) + (size_t)PX_WARPS * 2 * xstage) +
+                 (size_t)w * 2 * vstage;                                                            // [2][D][PG]
+  const int jbase = blockIdx.y * 32;
+  for (int t = threadIdx.x; t < C * KS * 32; t += blockDim.x) {
+    const int sl = t & 31, k = (t >> 5) % KS, c = (t >> 5) / KS;
+    const int j = jbase + sl % LG;
+    const bool on = j < N && k < a.tb.K[c];
+    const int64_t o = ((int64_t)c * Kmax + k) * Npad + (j < Npad ? j : 0);
+    // (padded lanes get one unit-mass component so they never look like an underflowed mixture)
+    sm_q[t] = make_float4(on ? a.tb.gs[o] : 0.f, on ? a.tb.gm[o] : 0.f,
+                          on ? a.tb.gc[o] + PxScale<KU>::SHIFT : (j < N || k > 0 ? -INFINITY : PxScale<KU>::SHIFT), 0.f);
+  }
+  __shared__ int sK[64];
+  for (int t = threadIdx.x; t < C; t += blockDim.x) sK[t] = a.tb.K[t];
+  for (int t = threadIdx.x; t < D * (Vmax + 1) * 32; t += blockDim.x) {
+    const int sl = t & 31, v = (t >> 5) % (Vmax + 1), d = (t >> 5) / (Vmax + 1);
+    const int j = jbase + sl % LG;
+    sm_cat[t] = j < N ? a.tb.cat[((int64_t)d * (Vmax + 1) + v) * Npad + j] : -INFINITY;
+  }
+  __syncthreads();
+  const int j = jbase + lj;
+  const int group = EPU * PG;                               // points per warp iteration
+  const int ngroups = (a.np + group - 1) / group;
+  const int64_t P = a.dv.P;
+  const int cstride = KS * 32, tstride = (Vmax + 1) * 32;
+  const bool lane_on = lp < PG && j < N;                    // lanes past the last whole group and padded states idle
+  const int lpc = lp < PG ? lp : 0;
+  const float *cont0 = a.dv.cont + a.p0;
+  const uint8_t *disc0 = a.dv.disc + a.p0;
+  // request group g's observations into stage st: piece i = (variable i / PG, lane group i % PG) is 4 consecutive
+  // points of one plane; lane l owns pieces l and l + 32 (the launcher keeps C PG and D PG <= 64) and holds their
+  // plane offsets.  Whole groups of aligned planes: one 16-byte cp.async per piece and one 4-byte cp.async per
+  // symbol piece; the ragged last group and unaligned planes: guarded loads and ordinary stores.
+  int64_t poff[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h, v = i / PG;
+    poff[h] = (int64_t)v * P + (i - v * PG) * EPU;
+  }
+  const int npx = C * PG, npv = D * PG;
+  auto request = [&](int g, int st) {
+    const int pb = g * group;
+    float4 *xd = xs + st * xstage;
+    uint32_t *vd = vs + st * vstage;
+    if (a.vec && pb + group <= a.np) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i < npx) cp_async16(xd + i, cont0 + poff[h] + pb);
+        if (i < npv) cp_async4(vd + i, disc0 + poff[h] + pb);
+      }
+    } else {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h, q = pb + (i % PG) * EPU;
+        if (i < npx) {
+          const float *src = cont0 + poff[h] + pb;
+          float x[EPU];
+#pragma unroll
+          for (int e = 0; e < EPU; ++e) x[e] = q + e < a.np ? __ldg(src + e) : 0.f;
+          xd[i] = make_float4(x[0], x[1], x[2], x[3]);
+        }
+        if (i < npv) {
+          const uint8_t *src = disc0 + poff[h] + pb;
+          uint32_t w4 = 0;
+#pragma unroll
+          for (int e = 0; e < EPU; ++e) w4 |= (q + e < a.np ? (uint32_t)__ldg(src + e) : (uint32_t)Vmax) << (8 * e);
+          vd[i] = w4;
+        }
+      }
+    }
+    cp_async_commit_px();
+  };
+  const int gstride = gridDim.x * PX_WARPS;
+  int g = blockIdx.x * PX_WARPS + w;
+  if (g < ngroups) request(g, 0);
+  for (int st = 0; g < ngroups; g += gstride, st ^= 1) {
+    cp_async_wait_px();
+    __syncwarp();                                            // stage st is complete; stage st ^ 1 is no longer read
+    if (g + gstride < ngroups) request(g + gstride, st ^ 1);
+    const float4 *xq = xs + st * xstage + lpc;                // this lane group's piece of variable 0; advanced per variable
+    const uint32_t *vq = vs + st * vstage + lpc;
+    u64 acc01 = 0ull, acc23 = 0ull, hold01 = 0ull, hold23 = 0ull;
+    const float4 *ps = sm_q + lane;
+    const float *tab = sm_cat + lane;
+    auto add_cat = [&]() {                                   // one symbol per byte; ids >= V mean "never seen"
+      const uint32_t w4 = *vq;
+      vq += PG;
+      float t[EPU];
+#pragma unroll
+      for (int i = 0; i < EPU; ++i) {
+        const int v = (int)__byte_perm(w4, 0u, 0x4440 + i);
+        t[i] = tab[(v < Vmax ? v : Vmax) * 32];
+      }
+      acc01 = add2(acc01, pk(t[0], t[1]));
+      acc23 = add2(acc23, pk(t[2], t[3]));
+      tab += tstride;
+    };
+    int c = 0;
+    if (KU > 0) {
+      for (; c + 1 < C; c += 2) {                            // pairs of variables share one log2
+        const float4 xa = xq[0], xb = xq[PG];
+        xq += 2 * PG;
+        emit_var_px<KU, 1>(ps, KU, pk(xa.x, xa.y), pk(xa.z, xa.w), acc01, acc23, hold01, hold23);
+        if (c < D) add_cat();
+        emit_var_px<KU, 2>(ps + cstride, KU, pk(xb.x, xb.y), pk(xb.z, xb.w), acc01, acc23, hold01, hold23);
+        if (c + 1 < D) add_cat();
+        ps += 2 * cstride;
+      }
+    }
+    for (; c < C; ++c) {
+      const float4 xa = xq[0];
+      xq += PG;
+      emit_var_px<KU, 0>(ps, KU > 0 ? KU : sK[c], pk(xa.x, xa.y), pk(xa.z, xa.w), acc01, acc23, hold01, hold23);
+      if (c < D) add_cat();
+      ps += cstride;
+    }
+    for (int d = C; d < D; ++d) add_cat();                   // more discrete than continuous variables
+    if (lane_on) {
+      const int q0 = g * group + lp * EPU;
+      const u64 ln2 = pk((float)DNBC_LN2, (float)DNBC_LN2);
+      float e[EPU];
+      unpk(mul2(acc01, ln2), e[0], e[1]);
+      unpk(mul2(acc23, ln2), e[2], e[3]);
+      float *dst = a.E + (int64_t)q0 * N + j;
+      if (q0 + EPU <= a.np) {
+#pragma unroll
+        for (int i = 0; i < EPU; ++i, dst += N) *dst = e[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPU; ++i, dst += N)
+          if (q0 + i < a.np) *dst = e[i];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // K3 statistics
 // ---------------------------------------------------------------------------------
 struct StatArgs {
@@ -728,6 +1006,17 @@ static void launch_emit_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem
   }
 }
 
+// points-packed kernel: component slots per variable and shared memory
+static size_t emit_px_smem(const Dims &d, int KS, int PG) {
+  const size_t stage = (size_t)d.C * PG * sizeof(float4) + (size_t)((d.D * PG + 3) & ~3) * sizeof(uint32_t);
+  return (size_t)d.C * KS * 32 * sizeof(float4) + (size_t)d.D * (d.Vmax + 1) * 32 * sizeof(float) + PX_WARPS * 2 * stage;
+}
+template <int KU>
+static void launch_emit_px_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_px<KU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_emission_px<KU><<<grid, PX_WARPS * 32, smem, c->stream>>>(a);
+}
+
 void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   if (np <= 0) return;
   FamTimer ft(c, FAM_EMISSION);
@@ -739,6 +1028,41 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   // the next group and store the same values.
   const int LG = lane_group(d, false);
   EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, LG, vec};
+  // The points-packed kernel takes every shape whose coefficients and staging fit its shared memory (measured against
+  // the component-packed one: 64.8 vs 67.1 ms per 3.2e7 points at the scale-out shape, 1.13 vs 1.62 ms per 2e7 points
+  // at N = 10, K = 3); the component-packed kernel remains for the rest.
+  bool uniform = d.C > 0;
+  for (int v = 0; v < d.C; ++v) uniform = uniform && c->K[v] == d.Kmax;
+#ifdef DNBC_EMIT_PX_NONE            // (A/B builds only: tools/build_variant.sh)
+  const bool pk_kernel = true;
+#else
+  const bool pk_kernel = false;
+#endif
+  const int KU = uniform && d.Kmax <= 8 ? d.Kmax : 0;
+  const size_t smem_px = emit_px_smem(d, KU > 0 ? KU : d.Kmax, 32 / LG);
+  if (!pk_kernel && smem_px <= 200 * 1024 && d.C * (32 / LG) <= 64 && d.D * (32 / LG) <= 64) {
+    const int gy = (d.N + 31) / 32;
+    int per_sm = (int)((200 * 1024) / (smem_px + 1024));
+    per_sm = per_sm > 2 ? 2 : per_sm;
+    const int64_t group = (int64_t)EPU * (32 / a.LG);
+    int64_t gx = (int64_t)c->sm_count * per_sm / gy;
+    const int64_t maxgx = ((np + group - 1) / group + 15) / 16;
+    gx = gx > maxgx ? maxgx : gx;
+    gx = gx < 1 ? 1 : gx;
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+    switch (KU) {
+      case 1: launch_emit_px_t<1>(c, a, grid, smem_px); break;
+      case 2: launch_emit_px_t<2>(c, a, grid, smem_px); break;
+      case 3: launch_emit_px_t<3>(c, a, grid, smem_px); break;
+      case 4: launch_emit_px_t<4>(c, a, grid, smem_px); break;
+      case 5: launch_emit_px_t<5>(c, a, grid, smem_px); break;
+      case 6: launch_emit_px_t<6>(c, a, grid, smem_px); break;
+      case 7: launch_emit_px_t<7>(c, a, grid, smem_px); break;
+      case 8: launch_emit_px_t<8>(c, a, grid, smem_px); break;
+      default: launch_emit_px_t<0>(c, a, grid, smem_px); break;
+    }
+    return;
+  }
   const size_t smem = emit_smem(d, KP);
   const int gy = (d.N + 31) / 32;                          // slices of 32 states that hold a real state
   int per_sm = (int)((200 * 1024) / (smem + 1024));

@@ -25,7 +25,16 @@
 
 namespace {
 
-constexpr int NW_MAX = 8;        // warps per CTA, one observed variable each
+#ifndef S2_NW
+#define S2_NW 8
+#endif
+#ifndef S2_WPSM
+#define S2_WPSM 16               // resident warps per SM the grid is sized for
+#endif
+constexpr int NW_MAX = S2_NW;    // warps per CTA, one observed variable each
+#ifndef S2_NOPIPE
+#define S2_NOPIPE 0              // 1: no software pipeline across points (A/B builds)
+#endif
 #ifndef S2_PTS
 #define S2_PTS 8                 // points per trip of the block loop (ptxas pays ~30 register moves per trip)
 #endif
@@ -227,22 +236,38 @@ __device__ __forceinline__ float block32(const Coef<KP, ODD> &q, Acc<KP, ODD> &a
   const int gstep = GRP ? gstep_ : 32, rstep = GRP ? rstep_ : 1;
   float hmax = 0.f;
   Pend<KP, ODD> pa, pb;
+#if !S2_NOPIPE
   if (HAS_C) {
-    const float4 r0 = *reinterpret_cast<const float4 *>(rec);
-    stage1<KP, ODD>(q, pk(r0.x, r0.y), pa);
+    const float r0 = *reinterpret_cast<const float *>(rec);
+    stage1<KP, ODD>(q, pk(r0, r0), pa);
   }
+#endif
   const float4 *rp = reinterpret_cast<const float4 *>(rec);
 #pragma unroll 1
   for (int it = 0; it < 32 / S2_PTS; ++it, rp += S2_PTS * rstep, gt += gstep * S2_PTS) {
 #pragma unroll
     for (int h = 0; h < S2_PTS; h += 2) {
       const float g0 = gt[gstep * h], g1 = gt[gstep * h + gstep];
+#if S2_NOPIPE
       if (HAS_C) {
-        const float2 x1 = *reinterpret_cast<const float2 *>(rp + (h + 1) * rstep);
-        stage1<KP, ODD>(q, pk(x1.x, x1.y), pb);
+        const float x0 = *reinterpret_cast<const float *>(rp + h * rstep);
+        const float x1 = *reinterpret_cast<const float *>(rp + (h + 1) * rstep);
+        Pend<KP, ODD> p0, p1;
+        stage1<KP, ODD>(q, pk(x0, x0), p0);
+        stage1<KP, ODD>(q, pk(x1, x1), p1);
+        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, p0, g0));
+        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, p1, g1));
+      }
+      if (false) {
+#else
+      if (HAS_C) {
+#endif
+        // (the observation enters the packed FMA as a scalar broadcast operand: FFMA2 R, R.F32, R.F32x2, R.F32x2)
+        const float x1 = *reinterpret_cast<const float *>(rp + (h + 1) * rstep);
+        stage1<KP, ODD>(q, pk(x1, x1), pb);
         hmax = fmaxf(hmax, stage2<KP, ODD>(acc, pa, g0));
-        const float2 x2 = *reinterpret_cast<const float2 *>(rp + (h + 2) * rstep);
-        stage1<KP, ODD>(q, pk(x2.x, x2.y), pa);
+        const float x2 = *reinterpret_cast<const float *>(rp + (h + 2) * rstep);
+        stage1<KP, ODD>(q, pk(x2, x2), pa);
         hmax = fmaxf(hmax, stage2<KP, ODD>(acc, pb, g1));
       }
       if (HAS_D) {
@@ -556,7 +581,7 @@ int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
   Stat2Args a{d, c->tables(), c->data(), p0, (int)nblk, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
               c->d_stats + sl.gamma, 4096, nw, LG, PG};
   const size_t smem = stats2_smem(d, nw, grp);
-  const int per_sm = 16 / nw > 8 ? 8 : 16 / nw;
+  const int per_sm = S2_WPSM / nw > 8 ? 8 : S2_WPSM / nw;
   int64_t gx = (int64_t)c->sm_count * per_sm / ((int64_t)gy * gz);
   const int64_t maxgx = (nblk + 7) / 8;
   if (gx > maxgx) gx = maxgx;
