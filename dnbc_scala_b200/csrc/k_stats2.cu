@@ -10,7 +10,7 @@
 // per (point, variable, 32 states) against 74 MUFU cycles: the sweep is ISSUE-bound, and 18 of the 73
 // are register moves, 64-bit address arithmetic and predicate bookkeeping around the posterior
 // prefetch (8 MOV, 3.7 IADD3, 3 FSETP, 1.4 LEA, 1 IMAD, 1 ISETP).  Here nothing is carried in
-// registers across points except the coefficients, the accumulators and the two pipeline buffers:
+// registers across points except the coefficients and the accumulators:
 //   * the posteriors of a 32-point x 32-state block arrive in shared memory through cp.async
 //     (8 x 16 B per lane per block, double buffered, one block ahead) and are read back with one
 //     conflict-free LDS per point: no prefetch registers, no rotation moves, no long-scoreboard stalls;
@@ -19,7 +19,7 @@
 //     packed pair (x, x) and the histogram row offset (no shuffle, no duplicate move);
 //   * blocks are always whole (the launcher gives the ragged tail to k_stats_pk), lanes are always
 //     real states: no predicates in the loop.
-// Per point and warp: 32 packed fp32 + 9 MUFU + ~13 other instructions.
+// Per point and warp at K = 8: 27 packed fp32 + 9 MUFU + ~10 other instructions.
 #include "dnbc_internal.cuh"
 #include "packed_f32.cuh"
 
@@ -32,11 +32,8 @@ namespace {
 #define S2_WPSM 16               // resident warps per SM the grid is sized for
 #endif
 constexpr int NW_MAX = S2_NW;    // warps per CTA, one observed variable each
-#ifndef S2_NOPIPE
-#define S2_NOPIPE 0              // 1: no software pipeline across points (A/B builds)
-#endif
 #ifndef S2_PTS
-#define S2_PTS 8                 // points per trip of the block loop (ptxas pays ~30 register moves per trip)
+#define S2_PTS 0                 // points per trip of the block loop; 0 = by mixture size (A/B builds set it)
 #endif
 
 struct Stat2Args {
@@ -220,55 +217,44 @@ __device__ __forceinline__ void shifted_point(const Coef<KP, ODD> &q, Acc<KP, OD
   }
 }
 
-// shared memory of one warp: posterior tiles (2 stages), observation records (2 stages, 33 entries: the pipeline
-// reads one record past the block), histogram rows
+// shared memory of one warp: posterior tiles (2 stages), observation records (2 stages), histogram rows
 struct alignas(16) Rec { float x0, x1; int voff; int pad; };
 
 // One 32-point block.  gt = this lane's column of the posterior tile (stride 32 floats per point), rec = the block's
 // observation records, bdb = this lane's histogram column as a byte address (rows are 128 bytes apart and the
-// record carries 128 * symbol).  Four points per loop trip with constant offsets from two bumped pointers; the two
-// pipeline buffers alternate, so nothing is copied between points.  Returns the largest weight g / sum seen.
+// record carries 128 * symbol).  PTS points per loop trip with constant offsets from two bumped pointers.
+// Nothing but the accumulators is carried from one trip to the next: the first version of this kernel software-
+// pipelined stage 1 of point p + 1 with stage 2 of point p through two loop-carried buffers, and at 128 registers
+// ptxas paid ~5 register moves per point for them at the back-edge.  Letting it schedule the PTS independent points of
+// a trip itself measures faster at every shape (scale-out 96.0 -> 89.4 ms per 3.2e7 points with 4 points per trip;
+// N = 512, K = 3: 9.93 -> 9.38 ms per 2.5e6 with 8; 16 and 32 are slower again, as are 96 or 80 registers with 20 or 24
+// warps per SM: 104.6 / 143.8 ms).  tools/pipe_peaks3.cu: the bare K = 8 body -- 27 packed + 9 MUFU + 4 scalar
+// instructions per point, no loads -- reaches 0.84 of the MUFU peak with 16 warps per SM; that, not 1.0, is the ceiling
+// of this instruction mix.  Packing the arithmetic over two POINTS of one component instead of two components of one
+// point (what k_emission_px does; no scalar tail for K = 3) was measured and dropped here: 9.68 vs 9.39 ms at N = 512,
+// 1.77 vs 1.69 ms at N = 10 -- two reciprocals and two clamps per pair cost more than the scalar tail they replace.
 // GRP (state counts up to 32): a warp step covers PG points x LG lanes, so a block is 32 steps = 32 PG points; gstep /
 // rstep are the distances between consecutive steps in the posterior tile (floats) and the record array.
 template <int KP, bool ODD, bool HAS_C, bool HAS_D, bool GRP>
 __device__ __forceinline__ float block32(const Coef<KP, ODD> &q, Acc<KP, ODD> &acc, const float *gt, const Rec *rec, char *bdb, float &gsl,
                                          bool gsum_on, int gstep_, int rstep_) {
+  constexpr int PTS = S2_PTS > 0 ? S2_PTS : (KP >= 4 ? 4 : 8);
   const int gstep = GRP ? gstep_ : 32, rstep = GRP ? rstep_ : 1;
   float hmax = 0.f;
-  Pend<KP, ODD> pa, pb;
-#if !S2_NOPIPE
-  if (HAS_C) {
-    const float r0 = *reinterpret_cast<const float *>(rec);
-    stage1<KP, ODD>(q, pk(r0, r0), pa);
-  }
-#endif
   const float4 *rp = reinterpret_cast<const float4 *>(rec);
 #pragma unroll 1
-  for (int it = 0; it < 32 / S2_PTS; ++it, rp += S2_PTS * rstep, gt += gstep * S2_PTS) {
+  for (int it = 0; it < 32 / PTS; ++it, rp += PTS * rstep, gt += gstep * PTS) {
 #pragma unroll
-    for (int h = 0; h < S2_PTS; h += 2) {
+    for (int h = 0; h < PTS; h += 2) {
       const float g0 = gt[gstep * h], g1 = gt[gstep * h + gstep];
-#if S2_NOPIPE
       if (HAS_C) {
+        // (the observation enters the packed FMA as a scalar broadcast operand: FFMA2 R, R.F32, R.F32x2, R.F32x2)
         const float x0 = *reinterpret_cast<const float *>(rp + h * rstep);
         const float x1 = *reinterpret_cast<const float *>(rp + (h + 1) * rstep);
         Pend<KP, ODD> p0, p1;
         stage1<KP, ODD>(q, pk(x0, x0), p0);
         stage1<KP, ODD>(q, pk(x1, x1), p1);
-        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, p0, g0));
-        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, p1, g1));
-      }
-      if (false) {
-#else
-      if (HAS_C) {
-#endif
-        // (the observation enters the packed FMA as a scalar broadcast operand: FFMA2 R, R.F32, R.F32x2, R.F32x2)
-        const float x1 = *reinterpret_cast<const float *>(rp + (h + 1) * rstep);
-        stage1<KP, ODD>(q, pk(x1, x1), pb);
-        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, pa, g0));
-        const float x2 = *reinterpret_cast<const float *>(rp + (h + 2) * rstep);
-        stage1<KP, ODD>(q, pk(x2, x2), pa);
-        hmax = fmaxf(hmax, stage2<KP, ODD>(acc, pb, g1));
+        hmax = fmaxf(hmax, fmaxf(stage2<KP, ODD>(acc, p0, g0), stage2<KP, ODD>(acc, p1, g1)));
       }
       if (HAS_D) {
         // categorical histogram: bins[symbol][state] += gamma
@@ -305,7 +291,7 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   if (!has_c && !has_d) return;
   const int TPB = 32 * PG;                                  // points per block
   const int tile_floats = GRP ? TPB * N : 32 * 32;
-  const int nrec = TPB + PG + 1;                            // (the pipeline reads one step past the block)
+  const int nrec = TPB + PG + 1;
   const int bin_floats = (Vmax + 1) * 32;
   const size_t per_warp = (size_t)2 * tile_floats * sizeof(float) + (size_t)2 * nrec * sizeof(Rec) + (size_t)(bin_floats + 4) * sizeof(float);
   unsigned char *base_w = smem_raw + (size_t)w * per_warp;
@@ -467,56 +453,33 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
       inwin = 0;
       if (has_c && lane_on) {
         const int K = a.tb.K[u];
+        // component k's window sums: z = (x - mu') s with mu' = -m/s the fp32-rounded centre; re-centre on the fp64
+        // old mean; sum r z^2 = c' S0 - sum r arg (stage2)
+        auto flush_one = [&](int k, float sv, float mv, float cv, double a0, double a1, double a2v) {
+          if (k >= K || a0 == 0.0) return;
+          const int64_t dst = ((int64_t)u * N + j) * Kmax + k;
+          const double s = (double)sv;
+          double m1 = 0.0, m2d = 0.0;
+          if (s > 0.0) {
+            const double delta = -(double)mv / s - a.mu_old[dst];
+            const double zz = (double)cv * a0 - a2v;
+            const double c1 = a1 / s, c2 = zz / (s * s);
+            m1 = c1 + delta * a0;
+            m2d = c2 + 2.0 * delta * c1 + delta * delta * a0;
+          }
+          atomicAdd(a.gmm + 3 * dst + 0, a0);
+          atomicAdd(a.gmm + 3 * dst + 1, m1);
+          atomicAdd(a.gmm + 3 * dst + 2, m2d);
+        };
 #pragma unroll
         for (int kp = 0; kp < KP; ++kp) {
           float sv[2], mv[2], cv[2], a0[2], a1[2], a2v[2];
           unpk(q.s2[kp], sv[0], sv[1]); unpk(q.m2[kp], mv[0], mv[1]); unpk(q.cc2[kp], cv[0], cv[1]);
           unpk(acc.S0[kp], a0[0], a0[1]); unpk(acc.S1[kp], a1[0], a1[1]); unpk(acc.S2[kp], a2v[0], a2v[1]);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int k = 2 * kp + h;
-            if (k < K && a0[h] != 0.f) {
-              // z = (x - mu') s with mu' = -m/s the fp32-rounded centre; re-centre on the fp64 old mean
-              const int64_t dst = ((int64_t)u * N + j) * Kmax + k;
-              const double s = (double)sv[h];
-              double m0 = (double)a0[h], m1 = 0.0, m2d = 0.0;
-              if (s > 0.0) {
-                const double delta = -(double)mv[h] / s - a.mu_old[dst];
-#if S2_TTRICK
-                const double zz = (double)cv[h] * (double)a0[h] - (double)a2v[h];   // sum r z^2 = c' S0 - sum r arg
-#else
-                const double zz = (double)a2v[h];
-#endif
-                const double c1 = (double)a1[h] / s, c2 = zz / (s * s);
-                m1 = c1 + delta * m0;
-                m2d = c2 + 2.0 * delta * c1 + delta * delta * m0;
-              }
-              atomicAdd(a.gmm + 3 * dst + 0, m0);
-              atomicAdd(a.gmm + 3 * dst + 1, m1);
-              atomicAdd(a.gmm + 3 * dst + 2, m2d);
-            }
-          }
+          for (int h = 0; h < 2; ++h) flush_one(2 * kp + h, sv[h], mv[h], cv[h], (double)a0[h], (double)a1[h], (double)a2v[h]);
         }
-        if (ODD && acc.t0 != 0.f) {
-          const int k = 2 * KP;
-          const int64_t dst = ((int64_t)u * N + j) * Kmax + k;
-          const double s = (double)q.s1;
-          double m0 = (double)acc.t0, m1 = 0.0, m2d = 0.0;
-          if (s > 0.0) {
-            const double delta = -(double)q.m1 / s - a.mu_old[dst];
-#if S2_TTRICK
-            const double zz = (double)q.c1 * (double)acc.t0 - (double)acc.t2;
-#else
-            const double zz = (double)acc.t2;
-#endif
-            const double c1 = (double)acc.t1 / s, c2 = zz / (s * s);
-            m1 = c1 + delta * m0;
-            m2d = c2 + 2.0 * delta * c1 + delta * delta * m0;
-          }
-          atomicAdd(a.gmm + 3 * dst + 0, m0);
-          atomicAdd(a.gmm + 3 * dst + 1, m1);
-          atomicAdd(a.gmm + 3 * dst + 2, m2d);
-        }
+        if (ODD) flush_one(2 * KP, q.s1, q.m1, q.c1, (double)acc.t0, (double)acc.t1, (double)acc.t2);
       }
       acc.t0 = acc.t1 = acc.t2 = 0.f;
 #pragma unroll
