@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECUDA, ENODEVICE, ESTATE, ENOMEM, ECOMM = range(7)
 COMM_ID_BYTES = 128
-OPT_MAX_CHUNK_POINTS, OPT_FB2_INTERLEAVE, OPT_FUSED_ESTEP = 1, 2, 3
+OPT_MAX_CHUNK_POINTS, OPT_FB2_INTERLEAVE, OPT_FUSED_ESTEP, OPT_FB_SEQ_LANES = 1, 2, 3, 4
 DECODE_REFERENCE, DECODE_BACKTRACE = 0, 1
 PREC_F32, PREC_F64 = 0, 1
 QUIRK_TRANSITIONS, DOUBLE_COUNT_FIRST = 1, 2

@@ -730,6 +730,10 @@ extern "C" int dnbc_set_option(dnbc_ctx *c, int option, int64_t value) {
       if (value < 0 || value > 2) return dnbc_fail(c, DNBC_EINVAL, "set_option: fused E-step mode must be 0, 1 or 2");
       c->opt_fused_estep = (int)value;
       return DNBC_OK;
+    case DNBC_OPT_FB_SEQ_LANES:
+      if (value < 0 || value > 2) return dnbc_fail(c, DNBC_EINVAL, "set_option: lane-per-sequence mode must be 0, 1 or 2");
+      c->opt_fb_seq_lanes = (int)value;
+      return DNBC_OK;
     default:
       return dnbc_fail(c, DNBC_EINVAL, "set_option: unknown option %d", option);
   }

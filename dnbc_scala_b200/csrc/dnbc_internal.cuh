@@ -120,6 +120,7 @@ struct dnbc_ctx {
   int64_t opt_max_chunk_points = 0;   // 0 = sized from the free memory
   bool opt_fb2_interleave = false;    // keep the four-sequences-per-lane-group recursions on small inputs
   int opt_fused_estep = 0;            // 0 auto, 1 always (when it fits), 2 never
+  int opt_fb_seq_lanes = 0;           // lane-per-sequence recursions (k_fbs.cu): 0 auto, 1 always (when N allows), 2 never
 
   // library-owned NCCL communicator (dnbc_comm.cu); void* keeps nccl.h out of the kernel files
   void *comm = nullptr;
@@ -193,6 +194,8 @@ void launch_fb3(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 bool fb2_supported(const dnbc_ctx *c);
 bool fb2_fuses_xi(const dnbc_ctx *c);
 void launch_fb2(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
+bool fbs_supported(const dnbc_ctx *c, int64_t nseq);
+void launch_fbs(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);
 bool viterbi_tile_supported(const dnbc_ctx *c);
 int launch_viterbi_tile(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path, double *score,
                         uint8_t *tie, uint16_t *bp);

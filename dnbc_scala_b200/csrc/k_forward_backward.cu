@@ -250,6 +250,7 @@ static void launch_fb_t(dnbc_ctx *c, const FbArgs &a, bool backward) {
 static void launch_fb(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward) {
   if (s1 <= s0) return;
   FamTimer ft(c, backward ? FAM_BACKWARD : FAM_FORWARD);
+  if (fbs_supported(c, s1 - s0)) return launch_fbs(c, s0, s1, p0, backward);   // small even N, many sequences: lane per sequence (k_fbs.cu)
   if (fb3_supported(c)) return launch_fb3(c, s0, s1, p0, backward);   // 33..64 states: mma.sync, 16 sequences per warp (k_fb3.cu)
   if (fb2_supported(c)) return launch_fb2(c, s0, s1, p0, backward);   // register-resident A (k_fb2.cu)
   if (fb_tc_supported(c)) {                                            // tcgen05 tensor cores (k_tc.cu)

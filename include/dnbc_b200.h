@@ -206,7 +206,11 @@ enum {
   /* E-step path for N <= 16: 0 = automatic (the single-launch kernel of k_fused.cu while its estimated time
    * is below the general pipeline's launch-latency floor -- it is latency-optimal, not throughput-optimal), 1 = always
    * the fused kernel when the shape fits its shared memory, 2 = always the general pipeline. */
-  DNBC_OPT_FUSED_ESTEP = 3
+  DNBC_OPT_FUSED_ESTEP = 3,
+  /* forward / backward recursions with one lane per sequence (even N <= 12, k_fbs.cu): 0 = automatic (chunks
+   * that give every SM scheduler a warp of 32 sequences), 1 = whenever the state count allows it (tests),
+   * 2 = never. */
+  DNBC_OPT_FB_SEQ_LANES = 4
 };
 int dnbc_set_option(dnbc_ctx *ctx, int option, int64_t value);
 

@@ -435,6 +435,54 @@ def test_fused_estep_outliers_and_long_sequences(oracle):
     assert abs(g2["ll"] - w2["ll"]) <= TOL * abs(w2["ll"])
 
 
+# ---------------------------------------------------------------------------------
+# even N <= 12: forward / backward with one lane per sequence (k_fbs.cu), forced on small inputs
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,V,K,lengths", [
+    (10, [10] * 5, [3, 1, 4, 2, 3], [200] * 9 + [37, 1, 0, 150] + [5, 6, 7, 8] * 9),   # config-1 variables, ragged, empty
+    (12, [4], [], [200] * 7 + [3] + list(range(1, 60))),                               # toy robot; two warps of sequences
+    (10, [], [3] * 5, [200] * 40),                                                     # config-3 shape
+    (2, [3], [2], [5, 1, 9, 4, 4, 4, 13]),
+    (4, [2, 2], [8], list(range(30, 70))),
+    (6, [5], [5, 7], [64] * 6 + [1] * 30),
+    (8, [6], [2], [90] * 5 + [3, 2, 1, 0, 0, 17]),
+])
+def test_lane_per_sequence_recursions_match_oracle(oracle, N, V, K, lengths):
+    """dnbc_set_option(DNBC_OPT_FB_SEQ_LANES, 1): the lane-per-sequence forward / backward kernels on inputs far below
+    their automatic threshold, against the fp64 oracle (statistics, posteriors, three EM iterations) and against
+    the lane-per-state kernels (mode 2); several chunks as well."""
+    m = random_model(oracle, N, V, K, 500 + N, transitions_per_state=min(N, 6))
+    data = sample(oracle, m, lengths, 510 + N)
+    q = perturb(oracle, m, 520 + N)
+    want = oracle.estep(q, data)
+    w3 = q.copy()
+    ll_want = oracle.em_iterate(w3, data, 3)
+    stats, post = {}, {}
+    for mode, chunk in ((1, 0), (2, 0), (1, max(data.P // 3, 256))):
+        with ctx_for(nat, q) as ctx:
+            ctx.set_option(nat.OPT_FUSED_ESTEP, 2)
+            ctx.set_option(nat.OPT_FB_SEQ_LANES, mode)
+            if chunk:
+                ctx.set_option(nat.OPT_MAX_CHUNK_POINTS, chunk)
+            upload(ctx, data, labels=False, dtype=np.float32)
+            ctx.em_estep()
+            got = ctx.em_get_stats()
+            if not chunk:
+                post[mode] = ctx.em_posteriors()
+            ll = ctx.em_iterate(3)
+            p = ctx.get_params()
+        stats[(mode, chunk)] = got
+        sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+        assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"]), (mode, chunk)
+        for key in ("pi", "xi", "gamma", "cat"):
+            np.testing.assert_allclose(sg[key], sw[key], rtol=1e-4, atol=1e-4, err_msg=f"{key} {mode} {chunk}")
+        np.testing.assert_allclose(ll, ll_want, rtol=TOL)
+        np.testing.assert_allclose(p["A"], w3.A, rtol=5e-4, atol=5e-5)
+        np.testing.assert_allclose(p["pi"], w3.pi, rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(post[1], post[2], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(post[1], oracle.posteriors(q, data), rtol=0, atol=5e-5)
+
+
 def test_state_counts_above_512(oracle):
     """N = 600 pads to 1024: beyond the tcgen05 recursion (256 / 512) and beyond the max-plus Viterbi tiles (two
     delta buffers of 32 sequences no longer fit one SM's shared memory), so the CTA-per-sequence kernels run."""

@@ -16,6 +16,8 @@ init = workloads.perturbed_params(wl, truth)
 ctx = nat.Context(wl.N, [wl.V] * wl.D, [wl.K] * wl.C, device=0)
 if len(sys.argv) > 4:
     ctx.set_option(nat.OPT_FUSED_ESTEP, int(sys.argv[4]))      # 1 = fused E-step kernel, 2 = general pipeline
+if os.environ.get("DNBC_FB_SEQ_LANES"):
+    ctx.set_option(nat.OPT_FB_SEQ_LANES, int(os.environ["DNBC_FB_SEQ_LANES"]))   # 1 = lane per sequence, 2 = lane per state
 ctx.set_params(truth["pi"], truth["A"], truth["B"], truth["w"], truth["mu"], truth["var"])
 ctx.generate(seqs, wl.T, 20260000 + wl.index * 1000)
 ctx.set_params(init["pi"], init["A"], init["B"], init["w"], init["mu"], init["var"])

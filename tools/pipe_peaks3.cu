@@ -22,7 +22,7 @@ __device__ __forceinline__ u64 ex2_2(u64 a) {
 }
 
 // OP 0: FFMA2 pair x scalar + scalar      OP 1: FFMA2 -pair x pair + scalar     OP 2: FFMA2 scalar x pair + pair
-// OP 3: FFMA2 three pairs                 OP 4: LDS.128 alone                   OP 5: LDS.64 alone
+// OP 3: FFMA2 three pairs                 (OP 4 / 5: shared-memory loads alone -- not run: the compiler keeps them out of the loop)
 // OP 6: 1 LDS.128 + 4 MUFU                OP 7: 4 MUFU alone
 // OP 8: points-packed body per component (LDS.128, 4 FFMA2, 4 MUFU, 2 FADD2)
 // OP 9: component-packed body per component pair (LDS.128 + LDS.64, 8 FFMA2, 8 MUFU, 4 FADD2)
@@ -178,8 +178,6 @@ int main() {
   run<1>("FFMA2 -pair x pair + scalar", 8, "instr-lanes", sms, mhz);
   run<2>("FFMA2 scalar x pair + pair", 8, "instr-lanes", sms, mhz);
   run<3>("FFMA2 three pairs", 8, "instr-lanes", sms, mhz);
-  run<4>("LDS.128 (conflict-free, + FADD2)", 8 * 16, "bytes", sms, mhz);
-  run<5>("LDS.64 (conflict-free, + FADD2)", 8 * 8, "bytes", sms, mhz);
   run<6>("1 LDS.128 + 4 MUFU", 32, "MUFU lane-ops", sms, mhz);
   run<7>("4 MUFU", 32, "MUFU lane-ops", sms, mhz);
   run<8>("points-packed body, K = 8 (per component: LDS.128, 4 FFMA2, 4 MUFU, 2 FADD2)", 32, "MUFU lane-ops", sms, mhz);
