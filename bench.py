@@ -441,6 +441,10 @@ def run_b200(args, wl):
             # whole step against the same pipe: every algorithmic transcendental of an iteration
             step_ops = wl.mufu_per_timestep
             roofline["step_frac"] = step_ops * seqs * wl.T / (step_ms * 1e-3 * sm_mhz * 1e6 * 148) / mufu_peak
+            # what the kernel's bare instruction mix reaches on this GPU (tools/pipe_peaks3.cu: no loads, no bookkeeping)
+            body = pipes.get("stats_body_mufu_frac" if top == "stats_gmm" else "emission_body_mufu_frac")
+            if body:
+                roofline["instruction_mix_ceiling_frac"] = float(body)
         else:
             roofline = dict(common, bound="hbm", achieved=hbm_achieved, peak=hbm_peak, unit="GB/s", frac=hbm_achieved / hbm_peak,
                             peak_source=which)
