@@ -149,6 +149,42 @@ def test_emission_f32_config1_shape(oracle):
     np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-5)
 
 
+@pytest.mark.parametrize("N,V,K,lengths", [
+    (64, [10] * 3, [8, 8], [33, 70, 1, 0, 64]),                  # uniform even K: log2 shared by the pair of variables
+    (64, [], [3, 3, 3], [50, 51]),                               # uniform odd K, odd variable count (pair + single)
+    (40, [4, 4, 4, 4], [2], [29, 3]),                            # more discrete than continuous variables, two state slices
+    (10, [6], [3, 1, 4, 2, 3, 5], [200, 37, 1, 0, 150, 13]),      # per-variable component counts, three points x 10 lanes
+    (12, [4], [], [200, 3, 5]),                                  # discrete only
+    (5, [3, 3], [7], [17] * 9),                                  # six lane groups of five states, K = 7
+    (2, [2] * 5, [2] * 5, [40] * 4),                             # 16 lane groups x 5 variables: beyond the staging, component-packed fallback
+    (512, [5] * 5, [3] * 5, [9, 8]),                             # config-5 variables
+])
+def test_emission_f32_every_dispatch_branch(oracle, N, V, K, lengths):
+    """k_emission_px (points-packed, cp.async staging) in each of its shapes -- uniform / per-variable component counts,
+    paired and single variables, lane groups below 32 states, ragged chunk ends and point counts that are not multiples
+    of four -- plus the component-packed fallback, against the fp64 oracle; outliers 30-60 sigma away take the
+    exponent-shifted path."""
+    m = random_model(oracle, N, V, K, 700 + N + len(K), transitions_per_state=min(N, 6))
+    data = sample(oracle, m, lengths, 710 + N)
+    if K:
+        rng = np.random.default_rng(720 + N)
+        hit = rng.choice(data.P, size=max(1, data.P // 9), replace=False)
+        data.cont[0, hit] += rng.choice([-1.0, 1.0], hit.size) * rng.uniform(30, 60, hit.size) * np.sqrt(m.var[0].max())
+        data = oracle.Data(data.off, data.disc, data.cont, data.labels)
+    want = oracle.emission_loglik(m, data)
+    with ctx_for(nat, m) as ctx:
+        upload(ctx, data, labels=False, dtype=np.float32)
+        got = ctx.emission_logprob(nat.PREC_F32)
+        path1, score1, _ = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+        ctx.set_option(nat.OPT_MAX_CHUNK_POINTS, 64)             # several chunks: starts that are not multiples of four
+        path2, score2, _ = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+    fin = np.isfinite(want)
+    assert (np.isfinite(got) == fin).all()
+    np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-5 * max(1, len(V) + len(K)) / 4)
+    np.testing.assert_array_equal(path1, path2)                  # the same emissions whatever the chunk's first point
+    np.testing.assert_array_equal(score1, score2)
+
+
 # ---------------------------------------------------------------------------------
 # K5 decode
 # ---------------------------------------------------------------------------------
