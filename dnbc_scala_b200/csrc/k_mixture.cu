@@ -339,7 +339,12 @@ __device__ __forceinline__ u64 lg2_2(u64 a) {
   return d;
 }
 // exponent-shifted evaluation of one (point, state, variable) whose mixture sum underflowed fp32: log2 of the sum
-// without the staged shift, finite wherever the reference's fp64 sum is finite (rare; kept out of line)
+// without the staged shift, finite wherever the reference's fp64 sum is finite; kept out of line.  Not rare with
+// hundreds of states: at N = 512 a quarter of the (4 points, variable, 32 states) groups have a state more than 11
+// sigma from every component at some point, and elimination builds put 29 % of the sweep's time here
+// (profiles/r02e_emission_elimination.jsonl).  Re-evaluating all four points of a flagged lane at once, packed, is
+// slower (9.36 vs 8.77 ms: usually one of the four is flagged); what helps is fewer and shorter evaluations --
+// emit_var_px's loop over each lane's next flagged point, and unrolled component loops here: 8.78 -> 8.06 ms.
 __device__ __noinline__ float emit_px_slow(const float4 *ps, int kc, float x, float shift) {
   float mx = -INFINITY;
   for (int k = 0; k < kc; ++k) {
@@ -354,6 +359,22 @@ __device__ __noinline__ float emit_px_slow(const float4 *ps, int kc, float x, fl
     const float z = fmaf(x, q.x, q.y);
     s += ex2_approx(fmaf(-z, z, q.z) - mx);
   }
+  return mx + lg2_approx(s) - shift;
+}
+// the same for a compile-time component count up to 4: unrolled, so the K coefficient loads and chains overlap
+template <int KU>
+__device__ __noinline__ float emit_px_slow_u(const float4 *ps, float x, float shift) {
+  float a[KU], mx = -INFINITY, s = 0.f;
+#pragma unroll
+  for (int k = 0; k < KU; ++k) {
+    const float4 q = ps[k * 32];
+    const float z = fmaf(x, q.x, q.y);
+    a[k] = fmaf(-z, z, q.z);
+    mx = fmaxf(mx, a[k]);
+  }
+  if (mx == -INFINITY) return -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KU; ++k) s += ex2_approx(a[k] - mx);
   return mx + lg2_approx(s) - shift;
 }
 // one variable, 4 points (x01, x23): log2 mixture density added to acc01 / acc23.  PAIR as in emit_var.
@@ -388,17 +409,40 @@ __device__ __forceinline__ void emit_var_px(const float4 *ps, int kc, u64 x01, u
   if (fminf(fminf(v[0], v[1]), fminf(v[2], v[3])) < PxScale<KU>::TINY) {
     // some point's mixture underflowed (every component > ~13 sigma away) or has no mass: its term is completed
     // here and it joins the log2 below as the neutral factor 2^SHIFT
+    // Each trip of the loop re-evaluates every lane's NEXT flagged point, whichever of the four it is: the number
+    // of (out-of-line, latency-bound) evaluations a warp pays is the largest count of flagged points in one lane,
+    // not the number of distinct flagged positions over its lanes.
     float x[4], ac[4];
     unpk(x01, x[0], x[1]);
     unpk(x23, x[2], x[3]);
     unpk(acc01, ac[0], ac[1]);
     unpk(acc23, ac[2], ac[3]);
+    if constexpr (KU <= 4) {
+      unsigned fl = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (v[i] < PxScale<KU>::TINY) {
-        ac[i] += emit_px_slow(ps, KU > 0 ? KU : kc, x[i], SH);
-        v[i] = KU > 0 ? 1073741824.f : 1.f;
+      for (int i = 0; i < 4; ++i) fl |= (v[i] < PxScale<KU>::TINY ? 1u : 0u) << i;
+      while (fl) {
+        const int i = __ffs(fl) - 1;
+        fl &= fl - 1;
+        const float xi = i == 0 ? x[0] : (i == 1 ? x[1] : (i == 2 ? x[2] : x[3]));
+        float L;
+        if constexpr (KU > 0) L = emit_px_slow_u<KU>(ps, xi, SH);
+        else L = emit_px_slow(ps, kc, xi, SH);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ac[e] += e == i ? L : 0.f;
+          v[e] = e == i ? (KU > 0 ? 1073741824.f : 1.f) : v[e];
+        }
       }
+    } else {                                                 // (large mixtures rarely underflow as a whole: the plain form
+                                                             // keeps the scale-out kernel's code as it measured fastest)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (v[i] < PxScale<KU>::TINY) {
+          ac[i] += emit_px_slow(ps, KU, x[i], SH);
+          v[i] = 1073741824.f;
+        }
+    }
     acc01 = pk(ac[0], ac[1]);
     acc23 = pk(ac[2], ac[3]);
     s01 = pk(v[0], v[1]);

@@ -162,14 +162,14 @@ def test_emission_f32_config1_shape(oracle):
 def test_emission_f32_every_dispatch_branch(oracle, N, V, K, lengths):
     """k_emission_px (points-packed, cp.async staging) in each of its shapes -- uniform / per-variable component counts,
     paired and single variables, lane groups below 32 states, ragged chunk ends and point counts that are not multiples
-    of four -- plus the component-packed fallback, against the fp64 oracle; outliers 30-60 sigma away take the
+    of four -- plus the component-packed fallback, against the fp64 oracle; outliers 14-30 sigma away take the
     exponent-shifted path."""
     m = random_model(oracle, N, V, K, 700 + N + len(K), transitions_per_state=min(N, 6))
     data = sample(oracle, m, lengths, 710 + N)
     if K:
         rng = np.random.default_rng(720 + N)
         hit = rng.choice(data.P, size=max(1, data.P // 9), replace=False)
-        data.cont[0, hit] += rng.choice([-1.0, 1.0], hit.size) * rng.uniform(30, 60, hit.size) * np.sqrt(m.var[0].max())
+        data.cont[0, hit] += rng.choice([-1.0, 1.0], hit.size) * rng.uniform(14, 30, hit.size) * np.sqrt(m.var[0].max())
         data = oracle.Data(data.off, data.disc, data.cont, data.labels)
     want = oracle.emission_loglik(m, data)
     with ctx_for(nat, m) as ctx:
@@ -179,7 +179,8 @@ def test_emission_f32_every_dispatch_branch(oracle, N, V, K, lengths):
         ctx.set_option(nat.OPT_MAX_CHUNK_POINTS, 64)             # several chunks: starts that are not multiples of four
         path2, score2, _ = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
     fin = np.isfinite(want)
-    assert (np.isfinite(got) == fin).all()
+    assert np.isfinite(got[fin]).all()                           # finite wherever the fp64 sum is ...
+    assert (got[~fin] < -700.0).all()                            # ... and below fp64's range (or -inf) where it is not
     np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-5 * max(1, len(V) + len(K)) / 4)
     np.testing.assert_array_equal(path1, path2)                  # the same emissions whatever the chunk's first point
     np.testing.assert_array_equal(score1, score2)
