@@ -28,7 +28,7 @@
 namespace {
 
 constexpr int FBS_WARPS = 4;
-constexpr int TB = 4;                                        // steps per staged tile
+constexpr int TB = 4;                                        // steps per staged tile (2 measured slower: 0.60 / 1.17 ms at N = 10)
 
 
 struct FbsArgs {
@@ -100,7 +100,7 @@ struct SeqDir {
 template <int N>
 struct CopyLane {
   static constexpr int PC = Geo<N>::PC, SPI = 32 / PC > 0 ? 32 / PC : 1;
-  static_assert(PC <= 32, "a tile row must fit one copy instruction");
+  static_assert(PC <= 32 && 32 % SPI == 0, "a copy instruction moves whole tile rows and the instructions tile the 32 rows");
   int q0, f, st;                                             // row within an instruction, float offset, step of the piece
   bool on;
   __device__ __forceinline__ CopyLane(int lane) : q0(lane / PC), f(2 * (lane % PC)), st(2 * (lane % PC) / N), on(lane < SPI * PC) {}

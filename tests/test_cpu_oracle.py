@@ -177,6 +177,16 @@ def test_library_exports_every_header_symbol():
     assert nat.lib().dnbc_abi_version() == 1
 
 
+def test_option_constants_match_the_header():
+    """dnbc_set_option's enumerators in include/dnbc_b200.h and the binding's OPT_* constants are the same numbers."""
+    from dnbc_scala_b200 import _native as nat
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "dnbc_b200.h")).read()
+    declared = {k: int(v) for k, v in re.findall(r"\bDNBC_(OPT_[A-Z0-9_]+)\s*=\s*(\d+)", hdr)}
+    assert len(declared) >= 4
+    for name, value in declared.items():
+        assert getattr(nat, name) == value, name
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product refuses to run (no oracle / CPU path behind the API)."""
     import torch
