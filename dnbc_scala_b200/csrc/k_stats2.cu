@@ -233,6 +233,8 @@ struct alignas(16) Rec { float x0, x1; int voff; int pad; };
 // of this instruction mix.  Packing the arithmetic over two POINTS of one component instead of two components of one
 // point (what k_emission_px does; no scalar tail for K = 3) was measured and dropped here: 9.68 vs 9.39 ms at N = 512,
 // 1.77 vs 1.69 ms at N = 10 -- two reciprocals and two clamps per pair cost more than the scalar tail they replace.
+// Packing only the odd last component over the two points of a trip: 9.42 vs 9.33 ms at N = 512, 1.67 vs 1.71 ms at
+// N = 10 -- within the noise either way, not kept.
 // GRP (state counts up to 32): a warp step covers PG points x LG lanes, so a block is 32 steps = 32 PG points; gstep /
 // rstep are the distances between consecutive steps in the posterior tile (floats) and the record array.
 template <int KP, bool ODD, bool HAS_C, bool HAS_D, bool GRP>
