@@ -64,251 +64,13 @@ struct EmitArgs {
 };
 
 constexpr int EPU = 4;   // points per thread and coefficient fetch
-
-// one variable, EPU points: log2 mixture density added to acc[]
-// kc = this variable's component count (warp-uniform): pairs past it are skipped, and the odd last
-// component is evaluated alone with scalar instructions -- K = 3 costs 3 exponentials, not 4.
-// VARK = false: every variable has exactly 2 KP components (no checks in the loop).
-// PAIR: the log2 is the second most frequent MUFU operation of the sweep (one per state, variable and point against
-// K exponentials), so two variables share one: PAIR = 1 keeps the first variable's mixture sums in hold[], PAIR = 2
-// adds log2(hold * sum) - 2 SHIFT, PAIR = 0 is a variable on its own (log2(sum) - SHIFT).  The staged log2 constants
-// carry SHIFT = EMIT_SHIFT when the kernel pairs (SHIFT = 0 otherwise), so a sum that passes the underflow test is
-// >= 1e-18 and the product of two cannot leave the fp32 range; the shift is taken back at once (an exact fp32
-// subtraction), so the accumulator keeps its small magnitude.  9,216 -> 8,704 MUFU operations per point at the
-// scale-out shape: 72.3 -> 66.8 ms per 3.2e7 points.  Only the uniform-K instantiation pairs: with per-variable
-// component counts (N = 512, K = 3) the three code variants cost more than the log2 they save (9.7 -> 10.5 ms).
+// The log2 is the second most frequent MUFU operation of the sweep (one per state, variable and point against K
+// exponentials), so two variables share one: the first variable's mixture sums are held, the second adds
+// log2(held * sum) - 2 SHIFT.  The staged log2 constants carry SHIFT = EMIT_SHIFT when the kernel pairs (0 otherwise),
+// so a sum that passes the underflow test is >= 1e-18 and the product of two cannot leave the fp32 range; the shift is
+// taken back at once (an exact fp32 subtraction), so the accumulator keeps its small magnitude.  9,216 -> 8,704 MUFU
+// operations per point at the scale-out shape: 72.3 -> 66.8 ms per 3.2e7 points.
 constexpr float EMIT_SHIFT = 30.f;       // log2 scale of the staged mixture constants of a pairing kernel
-template <bool VARK>
-struct EmitScale {
-  static constexpr float SHIFT = VARK ? 0.f : EMIT_SHIFT;
-  static constexpr float TINY = VARK ? 1e-30f : 1e-18f;   // sums below this take the exponent-shifted evaluation
-};
-template <int KP, bool VARK, int PAIR>
-__device__ __forceinline__ void emit_var(const float4 *ps, const float2 *pc, const float (&x)[EPU], float (&acc)[EPU], int kc,
-                                         float (&hold)[EPU]) {
-  const u64 neg1 = pk(-1.f, -1.f);
-  u64 xx[EPU], sum2[EPU];
-#pragma unroll
-  for (int i = 0; i < EPU; ++i) { xx[i] = pk(x[i], x[i]); sum2[i] = 0ull; }
-#pragma unroll
-  for (int kp = 0; kp < KP; ++kp) {
-    if (VARK && 2 * kp >= kc) break;
-    const float4 sm4 = ps[kp * 32];
-    const float2 cc = pc[kp * 32];
-    if (!VARK || 2 * kp + 1 < kc) {
-      const u64 s2 = pk(sm4.x, sm4.y), m2 = pk(sm4.z, sm4.w), cc2 = pk(cc.x, cc.y);
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) {
-        const u64 z2 = fma2(xx[i], s2, m2);
-        const u64 e2 = ex2_2(fnma2(z2, z2, cc2));
-        sum2[i] = kp == 0 ? e2 : add2(sum2[i], e2);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) {
-        const float z = fmaf(x[i], sm4.x, sm4.z);
-        const float e = ex2_approx(fmaf(-z, z, cc.x));
-        float lo, hi;
-        unpk(sum2[i], lo, hi);
-        sum2[i] = pk(lo + e, hi);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < EPU; ++i) {
-    constexpr float SH = EmitScale<VARK>::SHIFT;
-    float sum = hsum(sum2[i]);
-    bool slow = false;
-    if (sum < EmitScale<VARK>::TINY) {
-      float L;
-      // every component underflowed fp32 (> ~13 sigma away), or none has mass: redo with the
-      // exponents shifted by their maximum, so the result stays finite where the reference's fp64
-      // sum is finite.  Rare per (point, state, variable); the maximum is only computed here.
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int kp = 0; kp < KP; ++kp) {
-        const float4 sm4 = ps[kp * 32];
-        const float2 cc = pc[kp * 32];
-        const u64 z2 = fma2(xx[i], pk(sm4.x, sm4.y), pk(sm4.z, sm4.w));
-        mx = max3lohi(mx, fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y)));
-      }
-      if (mx != -INFINITY) {
-        u64 s = 0ull;
-        const u64 nm = pk(-mx, -mx);
-#pragma unroll 1
-        for (int kp = 0; kp < KP; ++kp) {
-          const float4 sm4 = ps[kp * 32];
-          const float2 cc = pc[kp * 32];
-          const u64 z2 = fma2(xx[i], pk(sm4.x, sm4.y), pk(sm4.z, sm4.w));
-          s = add2(s, ex2_2(add2(fma2(mul2(z2, z2), neg1, pk(cc.x, cc.y)), nm)));
-        }
-        L = mx + lg2_approx(hsum(s));
-      } else {
-        L = -INFINITY;                               // no component has mass
-      }
-      acc[i] += L - SH;                              // this variable's term is complete ...
-      sum = 1073741824.f;                            // ... and joins a pair as the neutral factor 2^EMIT_SHIFT
-      slow = true;
-    }
-    if (PAIR == 1) hold[i] = sum;
-    else if (PAIR == 2) acc[i] += lg2_approx(hold[i] * sum) - 2.f * SH;
-    else if (!slow) acc[i] += lg2_approx(sum) - SH;
-  }
-}
-
-// shared-memory coefficient block of one 32-state slice: [C][KP][32] x {s.lo,s.hi,m.lo,m.hi} then
-// [C][KP][32] x {cc.lo,cc.hi}, then the categorical table [D][Vmax+1][32]
-template <int KP, bool VARK>
-__global__ void __launch_bounds__(512, 2) k_emission_pk(EmitArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
-  const int LG = a.LG, PG = 32 / LG;
-  float4 *sm_sm = (float4 *)smraw;                          // [C*KP*32]
-  float2 *sm_cc = (float2 *)(sm_sm + (size_t)C * KP * 32);  // [C*KP*32]
-  float *sm_cat = (float *)(sm_cc + (size_t)C * KP * 32);   // [D*(Vmax+1)*32]
-  const int lane = threadIdx.x & 31, lj = lane % LG, lp = lane / LG;
-  const int jbase = blockIdx.y * 32;
-  // stage this slice's coefficients (column index = lane slot; slots of the same state repeat)
-  for (int t = threadIdx.x; t < C * KP * 32; t += blockDim.x) {
-    const int sl = t & 31, kp = (t >> 5) % KP, c = (t >> 5) / KP;
-    const int j = jbase + sl % LG;
-    float v[6];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k = 2 * kp + h;
-      const bool on = j < N && k < a.tb.K[c];
-      const int64_t o = ((int64_t)c * Kmax + (k < Kmax ? k : 0)) * Npad + (j < Npad ? j : 0);
-      v[h] = on ? a.tb.gs[o] : 0.f;
-      v[2 + h] = on ? a.tb.gm[o] : 0.f;
-      // (padded lanes get unit-mass components so they never look like an underflowed mixture)
-      v[4 + h] = on ? a.tb.gc[o] + EmitScale<VARK>::SHIFT : (j < N ? -INFINITY : 0.f);
-    }
-    sm_sm[t] = make_float4(v[0], v[1], v[2], v[3]);
-    sm_cc[t] = make_float2(v[4], v[5]);
-  }
-  __shared__ int sK[64];                                     // components per continuous variable (C <= 64 here)
-  for (int t = threadIdx.x; t < C; t += blockDim.x) sK[t] = a.tb.K[t];
-  for (int t = threadIdx.x; t < D * (Vmax + 1) * 32; t += blockDim.x) {
-    const int sl = t & 31, v = (t >> 5) % (Vmax + 1), d = (t >> 5) / (Vmax + 1);
-    const int j = jbase + sl % LG;
-    sm_cat[t] = j < N ? a.tb.cat[((int64_t)d * (Vmax + 1) + v) * Npad + j] : -INFINITY;
-  }
-  __syncthreads();
-  const int j = jbase + lj;
-  const int group = EPU * PG;                               // points per warp iteration
-  const int ngroups = (a.np + group - 1) / group;
-  const int wpb = blockDim.x >> 5;
-  const float *cont0 = a.dv.cont + a.p0;
-  const uint8_t *disc0 = a.dv.disc + a.p0;
-  const int64_t P = a.dv.P;
-  const bool vec = a.vec && PG == 1;
-  const int cstride = KP * 32;
-  const int tstride = (Vmax + 1) * 32;
-  for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * wpb) {
-    const int pb = g * group;
-    const bool full = pb + group <= a.np;
-    float acc[EPU];
-#pragma unroll
-    for (int i = 0; i < EPU; ++i) acc[i] = 0.f;
-    const float4 *ps = sm_sm + lane;
-    const float2 *pc = sm_cc + lane;
-    const float *tab = sm_cat + lane;
-    auto add_cat = [&](uint32_t w4) {                        // one symbol per byte; ids >= V mean "never seen"
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) {
-        const int v = (int)__byte_perm(w4, 0u, 0x4440 + i);
-        acc[i] += tab[(v < Vmax ? v : Vmax) * 32];
-      }
-      tab += tstride;
-    };
-    // variable c + 1's observations (and discrete variable c + 1's symbols) are fetched while
-    // variable c is evaluated, so no load latency is exposed
-    float xc[EPU], xn[EPU];
-    uint32_t vc = 0, vn = 0;
-    if (vec && full) {
-      // fast path: 4 consecutive points per lane, one 16-byte and one 4-byte load per variable, the
-      // plane pointers advanced by P per variable (no per-variable address arithmetic or predicates)
-      const float *xp = cont0 + pb;
-      const uint8_t *vp = disc0 + pb;
-      auto ldx = [&](float (&x)[EPU]) {
-        const float4 v = __ldg((const float4 *)xp);
-        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-      };
-      if (C > 0) ldx(xc);
-      if (D > 0) vc = __ldg((const uint32_t *)vp);
-      float hold[EPU];
-      for (int c = 0; c < C; ++c) {
-        xp += P;
-        vp += P;
-        if (c + 1 < C) ldx(xn);
-        if (c + 1 < D) vn = __ldg((const uint32_t *)vp);
-        if (VARK) emit_var<KP, VARK, 0>(ps, pc, xc, acc, sK[c], hold);
-        else if (c & 1) emit_var<KP, VARK, 2>(ps, pc, xc, acc, sK[c], hold);
-        else if (c + 1 < C) emit_var<KP, VARK, 1>(ps, pc, xc, acc, sK[c], hold);
-        else emit_var<KP, VARK, 0>(ps, pc, xc, acc, sK[c], hold);
-        ps += cstride;
-        pc += cstride;
-        if (c < D) add_cat(vc);
-#pragma unroll
-        for (int i = 0; i < EPU; ++i) xc[i] = xn[i];
-        vc = vn;
-      }
-      for (int d = C; d < D; ++d) {                          // more discrete than continuous variables
-        vp += P;                                             // (vp pointed at variable d's plane)
-        if (d + 1 < D) vn = __ldg((const uint32_t *)vp);
-        add_cat(vc);
-        vc = vn;
-      }
-      if (j < N) {
-        float *dst = a.E + (int64_t)pb * N + j;
-#pragma unroll
-        for (int i = 0; i < EPU; ++i) dst[(int64_t)i * N] = acc[i] * (float)DNBC_LN2;
-      }
-      continue;
-    }
-    int po[EPU];                                            // this lane's points (chunk-relative)
-#pragma unroll
-    for (int i = 0; i < EPU; ++i) po[i] = pb + i * PG + lp;
-    auto load_x = [&](int c, float (&x)[EPU]) {
-      const float *col = cont0 + (int64_t)c * P;
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) x[i] = po[i] < a.np ? __ldg(col + po[i]) : 0.f;
-    };
-    auto load_v = [&](int d) -> uint32_t {
-      const uint8_t *col = disc0 + (int64_t)d * P;
-      uint32_t w4 = 0;
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) w4 |= (po[i] < a.np ? (uint32_t)__ldg(col + po[i]) : (uint32_t)Vmax) << (8 * i);
-      return w4;
-    };
-    if (C > 0) load_x(0, xc);
-    if (D > 0) vc = load_v(0);
-#pragma unroll 1
-    for (int c = 0; c < C; ++c) {
-      if (c + 1 < C) load_x(c + 1, xn);
-      if (c + 1 < D) vn = load_v(c + 1);
-      emit_var<KP, VARK, 0>(ps, pc, xc, acc, sK[c], xn);      // (general path: every variable on its own; xn is not read)
-      ps += cstride;
-      pc += cstride;
-      if (c < D) add_cat(vc);
-#pragma unroll
-      for (int i = 0; i < EPU; ++i) xc[i] = xn[i];
-      vc = vn;
-    }
-#pragma unroll 1
-    for (int d = C; d < D; ++d) {                           // more discrete than continuous variables
-      if (d + 1 < D) vn = load_v(d + 1);
-      add_cat(vc);
-      vc = vn;
-    }
-    if (j < N) {
-      float *dst = a.E + (int64_t)pb * N + j;
-#pragma unroll
-      for (int i = 0; i < EPU; ++i)
-        if (po[i] < a.np) dst[(int64_t)(i * PG + lp) * N] = acc[i] * (float)DNBC_LN2;
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------
 // K1 emission, packed over POINTS (k_emission_px)
@@ -525,20 +287,22 @@ __global__ void __launch_bounds__(PX_WARPS * 32, 2) k_emission_px(EmitArgs a) {
   const float *cont0 = a.dv.cont + a.p0;
   const uint8_t *disc0 = a.dv.disc + a.p0;
   // request group g's observations into stage st: piece i = (variable i / PG, lane group i % PG) is 4 consecutive
-  // points of one plane; lane l owns pieces l and l + 32 (the launcher keeps C PG and D PG <= 64) and holds their
-  // plane offsets.  Whole groups of aligned planes: one 16-byte cp.async per piece and one 4-byte cp.async per
+  // points of one plane; lane l owns pieces l, l + 32, ... and holds the plane offsets of its first two (shapes with
+  // more than 64 pieces -- many variables x many lane groups -- compute the rest on the fly).  Whole groups of aligned planes: one 16-byte cp.async per piece and one 4-byte cp.async per
   // symbol piece; the ragged last group and unaligned planes: guarded loads and ordinary stores.
+  auto piece_off = [&](int i) -> int64_t {
+    const int v = i / PG;
+    return (int64_t)v * P + (i - v * PG) * EPU;
+  };
   int64_t poff[2];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int i = lane + 32 * h, v = i / PG;
-    poff[h] = (int64_t)v * P + (i - v * PG) * EPU;
-  }
+  for (int h = 0; h < 2; ++h) poff[h] = piece_off(lane + 32 * h);
   const int npx = C * PG, npv = D * PG;
   auto request = [&](int g, int st) {
     const int pb = g * group;
     float4 *xd = xs + st * xstage;
     uint32_t *vd = vs + st * vstage;
+    const int npmax = npx > npv ? npx : npv;
     if (a.vec && pb + group <= a.np) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -546,19 +310,25 @@ __global__ void __launch_bounds__(PX_WARPS * 32, 2) k_emission_px(EmitArgs a) {
         if (i < npx) cp_async16(xd + i, cont0 + poff[h] + pb);
         if (i < npv) cp_async4(vd + i, disc0 + poff[h] + pb);
       }
+      for (int i = lane + 64; i < npmax; i += 32) {            // (many variables x many lane groups: offsets on the fly)
+        const int64_t off = piece_off(i) + pb;
+        if (i < npx) cp_async16(xd + i, cont0 + off);
+        if (i < npv) cp_async4(vd + i, disc0 + off);
+      }
     } else {
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int i = lane + 32 * h, q = pb + (i % PG) * EPU;
+      for (int i = lane; i < npmax; i += 32) {
+        const int q = pb + (i % PG) * EPU;
+        const int64_t off = piece_off(i) + pb;
         if (i < npx) {
-          const float *src = cont0 + poff[h] + pb;
+          const float *src = cont0 + off;
           float x[EPU];
 #pragma unroll
           for (int e = 0; e < EPU; ++e) x[e] = q + e < a.np ? __ldg(src + e) : 0.f;
           xd[i] = make_float4(x[0], x[1], x[2], x[3]);
         }
         if (i < npv) {
-          const uint8_t *src = disc0 + poff[h] + pb;
+          const uint8_t *src = disc0 + off;
           uint32_t w4 = 0;
 #pragma unroll
           for (int e = 0; e < EPU; ++e) w4 |= (q + e < a.np ? (uint32_t)__ldg(src + e) : (uint32_t)Vmax) << (8 * e);
@@ -1012,10 +782,6 @@ __global__ void __launch_bounds__(DNBC_STATS_NW * 32, DNBC_STATS_OCC) k_stats_pk
 // ---------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------
-static size_t emit_smem(const Dims &d, int KP) {
-  return (size_t)d.C * KP * 32 * (sizeof(float4) + sizeof(float2)) + (size_t)d.D * (d.Vmax + 1) * 32 * sizeof(float);
-}
-
 // Lanes per group of states in the emission / statistics sweeps.  Normally the padded (power-of-two) state
 // count, so that groups tile the warp; the exact state count when that puts more points into a warp
 // (N = 10: 3 x 10 lanes instead of 2 x 16; N = 5: 6 x 5 instead of 4 x 8).
@@ -1025,10 +791,6 @@ static int lane_group(const Dims &d, bool pow2_only) {
   return (!pow2_only && pg_exact > pg_pad) ? d.N : (d.Npad < 32 ? d.Npad : 32);
 }
 
-bool mixture_emission_fast(const dnbc_ctx *c) {
-  const int KP = (c->dm.Kmax + 1) / 2;
-  return KP <= 4 && c->dm.C <= 64 && emit_smem(c->dm, KP) <= 100 * 1024;
-}
 // the statistics sweep keeps 3K coefficients + 3K accumulators in registers and handles one
 // continuous and one discrete variable per warp
 bool mixture_stats_fast(const dnbc_ctx *c) {
@@ -1037,23 +799,22 @@ bool mixture_stats_fast(const dnbc_ctx *c) {
   return d.Kmax <= 8 && units <= 64 && (size_t)8 * (d.Vmax + 1) * 32 * sizeof(float) <= 96 * 1024;
 }
 
-template <int KP>
-static void launch_emit_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem) {
-  bool vark = false;                                         // some variable with fewer than 2 KP components?
-  for (int v = 0; v < c->dm.C; ++v) vark = vark || c->K[v] != 2 * KP;
-  if (vark) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_emission_pk<KP, true><<<grid, 512, smem, c->stream>>>(a);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_pk<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_emission_pk<KP, false><<<grid, 512, smem, c->stream>>>(a);
-  }
-}
-
 // points-packed kernel: component slots per variable and shared memory
 static size_t emit_px_smem(const Dims &d, int KS, int PG) {
   const size_t stage = (size_t)d.C * PG * sizeof(float4) + (size_t)((d.D * PG + 3) & ~3) * sizeof(uint32_t);
   return (size_t)d.C * KS * 32 * sizeof(float4) + (size_t)d.D * (d.Vmax + 1) * 32 * sizeof(float) + PX_WARPS * 2 * stage;
+}
+// emission through k_emission_px: up to 8 components per mixture, coefficients + staging within one SM's shared memory
+// (everything else takes the generic kernel of k_emission.cu)
+static int emit_px_ku(const dnbc_ctx *c) {                   // the common component count, or 0 (per-variable counts)
+  bool uniform = c->dm.C > 0;
+  for (int v = 0; v < c->dm.C; ++v) uniform = uniform && c->K[v] == c->dm.Kmax;
+  return uniform ? c->dm.Kmax : 0;
+}
+bool mixture_emission_fast(const dnbc_ctx *c) {
+  const Dims &d = c->dm;
+  const int KU = emit_px_ku(c);
+  return d.Kmax <= 8 && d.C <= 64 && emit_px_smem(d, KU > 0 ? KU : d.Kmax, 32 / lane_group(d, false)) <= 200 * 1024;
 }
 template <int KU>
 static void launch_emit_px_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem) {
@@ -1065,64 +826,33 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   if (np <= 0) return;
   FamTimer ft(c, FAM_EMISSION);
   const Dims &d = c->dm;
-  const int KP = (d.Kmax + 1) / 2;
   const int vec = (c->P % 4 == 0) && (p0 % 4 == 0);
   // lane group = the state count itself when it is below 32 (N = 10: three points x 10 states fill 30 lanes;
   // the power-of-two group of 16 would fill 20).  Lanes past the last whole group repeat the first points of
   // the next group and store the same values.
   const int LG = lane_group(d, false);
   EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, LG, vec};
-  // The points-packed kernel takes every shape whose coefficients and staging fit its shared memory (measured against
-  // the component-packed one: 64.8 vs 67.1 ms per 3.2e7 points at the scale-out shape, 1.13 vs 1.62 ms per 2e7 points
-  // at N = 10, K = 3); the component-packed kernel remains for the rest.
-  bool uniform = d.C > 0;
-  for (int v = 0; v < d.C; ++v) uniform = uniform && c->K[v] == d.Kmax;
-#ifdef DNBC_EMIT_PX_NONE            // (A/B builds only: tools/build_variant.sh)
-  const bool pk_kernel = true;
-#else
-  const bool pk_kernel = false;
-#endif
-  const int KU = uniform && d.Kmax <= 8 ? d.Kmax : 0;
+  const int KU = emit_px_ku(c);
   const size_t smem_px = emit_px_smem(d, KU > 0 ? KU : d.Kmax, 32 / LG);
-  if (!pk_kernel && smem_px <= 200 * 1024 && d.C * (32 / LG) <= 64 && d.D * (32 / LG) <= 64) {
-    const int gy = (d.N + 31) / 32;
-    int per_sm = (int)((200 * 1024) / (smem_px + 1024));
-    per_sm = per_sm > 2 ? 2 : per_sm;
-    const int64_t group = (int64_t)EPU * (32 / a.LG);
-    int64_t gx = (int64_t)c->sm_count * per_sm / gy;
-    const int64_t maxgx = ((np + group - 1) / group + 15) / 16;
-    gx = gx > maxgx ? maxgx : gx;
-    gx = gx < 1 ? 1 : gx;
-    const dim3 grid((unsigned)gx, (unsigned)gy);
-    switch (KU) {
-      case 1: launch_emit_px_t<1>(c, a, grid, smem_px); break;
-      case 2: launch_emit_px_t<2>(c, a, grid, smem_px); break;
-      case 3: launch_emit_px_t<3>(c, a, grid, smem_px); break;
-      case 4: launch_emit_px_t<4>(c, a, grid, smem_px); break;
-      case 5: launch_emit_px_t<5>(c, a, grid, smem_px); break;
-      case 6: launch_emit_px_t<6>(c, a, grid, smem_px); break;
-      case 7: launch_emit_px_t<7>(c, a, grid, smem_px); break;
-      case 8: launch_emit_px_t<8>(c, a, grid, smem_px); break;
-      default: launch_emit_px_t<0>(c, a, grid, smem_px); break;
-    }
-    return;
-  }
-  const size_t smem = emit_smem(d, KP);
-  const int gy = (d.N + 31) / 32;                          // slices of 32 states that hold a real state
-  int per_sm = (int)((200 * 1024) / (smem + 1024));
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
+  const int gy = (d.N + 31) / 32;                            // slices of 32 states that hold a real state
+  int per_sm = (int)((200 * 1024) / (smem_px + 1024));
+  per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);
   const int64_t group = (int64_t)EPU * (32 / a.LG);
   int64_t gx = (int64_t)c->sm_count * per_sm / gy;
   const int64_t maxgx = ((np + group - 1) / group + 15) / 16;
-  if (gx > maxgx) gx = maxgx;
-  if (gx < 1) gx = 1;
+  gx = gx > maxgx ? maxgx : gx;
+  gx = gx < 1 ? 1 : gx;
   const dim3 grid((unsigned)gx, (unsigned)gy);
-  switch (KP) {
-    case 1: launch_emit_t<1>(c, a, grid, smem); break;
-    case 2: launch_emit_t<2>(c, a, grid, smem); break;
-    case 3: launch_emit_t<3>(c, a, grid, smem); break;
-    default: launch_emit_t<4>(c, a, grid, smem); break;
+  switch (KU) {
+    case 1: launch_emit_px_t<1>(c, a, grid, smem_px); break;
+    case 2: launch_emit_px_t<2>(c, a, grid, smem_px); break;
+    case 3: launch_emit_px_t<3>(c, a, grid, smem_px); break;
+    case 4: launch_emit_px_t<4>(c, a, grid, smem_px); break;
+    case 5: launch_emit_px_t<5>(c, a, grid, smem_px); break;
+    case 6: launch_emit_px_t<6>(c, a, grid, smem_px); break;
+    case 7: launch_emit_px_t<7>(c, a, grid, smem_px); break;
+    case 8: launch_emit_px_t<8>(c, a, grid, smem_px); break;
+    default: launch_emit_px_t<0>(c, a, grid, smem_px); break;
   }
 }
 

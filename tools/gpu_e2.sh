@@ -1,15 +1,7 @@
 #!/bin/bash
-# round-2 GPU call E7: k_stats2 with the odd last component of two points as one packed chain, against the previous commit
+# round-2 GPU call E8: ncu of the N = 64 Viterbi kernels (k_viterbi2 / k_backtrace)
 mkdir -p gpurun_out
-rm -f gpurun_out/e7_kbench.jsonl
-timeout 900 python -m pytest tests -m gpu -q -x -k "estep or stats or config5 or fused_and_general or randomised or outlier or lane_per" > gpurun_out/e7_pytest.log 2>&1; tail -3 gpurun_out/e7_pytest.log
-for w in "largeN 12500 3" "gmm100k 100000 3 2" "readme 16000 3 2"; do
-for lib in "" build/libdnbc_s2prev.so "" build/libdnbc_s2prev.so; do
-  DNBC_B200_LIB=$lib python tools/kbench.py $w >> gpurun_out/e7_kbench.jsonl 2>> gpurun_out/e7_err.log
-done
-done
-python - <<'PY'
-import json
-for l in open('gpurun_out/e7_kbench.jsonl'):
-    d = json.loads(l); print(d['lib'], d['workload'], d['ms_per_iter']['stats_gmm'], d['ll'])
-PY
+python tools/dbench.py scaleout 32000 | cut -c1-250
+ncu --set full --clock-control none --import-source on -k "regex:k_viterbi2|k_backtrace" -c 2 -o gpurun_out/prof_r02e_vit -f python tools/dbench.py scaleout 8000 > gpurun_out/e8_ncu.log 2>&1; tail -1 gpurun_out/e8_ncu.log
+python tools/ncu_summary.py gpurun_out/prof_r02e_vit.ncu-rep --ops > gpurun_out/r02e_ncu_viterbi2_summary.txt; cat gpurun_out/r02e_ncu_viterbi2_summary.txt | cut -c1-400
+ncu -i gpurun_out/prof_r02e_vit.ncu-rep --page source --csv --print-source sass | gzip > gpurun_out/r02e_src_vit.csv.gz
