@@ -1,6 +1,6 @@
 // k_mixture.cu -- the two Gaussian-mixture sweeps of an EM iteration.
 //
-//   k_emission_pk (K1): E[p][j] = ln P(o_p | state j)
+//   k_emission_px (K1): E[p][j] = ln P(o_p | state j)
 //       reference arithmetic: emissionsSum of viterbiInitialize / viterbiCompute,
 //       core/src/main/scala/DynamicNaiveBayesianClassifier.scala:52-56, 79-83;
 //       LearnedDiscreteEdge.probability Edge.scala:69-75; LearnedContinuousEdge.probability
@@ -14,16 +14,16 @@
 // point: ~8.2k exponentials per point at the scale-out shape against 80 B of observations, so
 // they are bound by the MUFU pipe (measured 16 ex2/clk/SM, tools/pipe_peaks.cu) and by
 // instruction issue, not by HBM.  Design rules that follow from the measurements:
-//   * fp32 work is issued as PACKED f32x2 instructions (FFMA2 / FMUL2 / FADD2, two mixture
-//     components per instruction): the FP32 pipe rate is unchanged but the issue slots per
-//     component halve, which is what lets MUFU run near its peak (tools/pipe_peaks2.cu: a body
-//     of 1 MUFU + 8 fp32 ops reaches 96 % of MUFU peak packed, 79 % scalar);
+//   * fp32 work is issued as PACKED f32x2 instructions (FFMA2 / FMUL2 / FADD2; the halves are two points of
+//     one component in the emission sweep, two components of one point in the statistics sweep): the FP32 pipe
+//     rate is unchanged but the issue slots halve, which is what lets MUFU run near its peak
+//     (tools/pipe_peaks2.cu: a body of 1 MUFU + 8 fp32 ops reaches 96 % of MUFU peak packed, 79 % scalar);
 //   * lanes run over hidden states (32 per warp; several points per warp when N <= 16), so
 //     parameter fetches are conflict-free and E / gamma rows are read and written as whole
 //     128-byte lines;
-//   * emission: every warp evaluates all variables for its own 4 points; coefficients stream
-//     from shared memory (one LDS.128 + one LDS.64 per component pair, amortised over the 4
-//     points); no barriers, no cross-warp traffic, high occupancy;
+//   * emission: every warp evaluates all variables for its own 4 points per lane group; coefficients stream
+//     from shared memory (one LDS.128 per component, amortised over the 4 points), observations arrive through
+//     cp.async one group ahead; no block barriers, no cross-warp traffic, high occupancy;
 //   * statistics: one warp per variable keeps that variable's coefficients AND its 3K moment
 //     accumulators in registers (fp32 over a window of <= 4096 points, in the standardised
 //     variable z and re-centred on the fp64 old mean when flushed: no x^2 - mu^2 cancellation);
@@ -84,9 +84,9 @@ constexpr float EMIT_SHIFT = 30.f;       // log2 scale of the staged mixture con
 //     arguments, packed accumulation; one underflow test per variable covers the four points;
 //   * lane groups below 32 states (N = 10: three points x 10 lanes) read 4 consecutive points per lane with one
 //     16-byte load like the full-warp layout does.
-// ncu before (profiles/r02t_ncu_n512_summary.txt, N = 512, K = 3): 40 warp instructions per (point, variable,
-// 32 states), issue 77 %, MUFU 63 %; the component-packed kernel stays in use where every variable has the same
-// EVEN component count (the scale-out shape: MUFU 90 %).
+// ncu of the component-packed kernel this one replaced (profiles/r02t_ncu_n512_summary.txt, N = 512, K = 3): 40 warp
+// instructions per (point, variable, 32 states), issue 77 %, MUFU 63 %; at the scale-out shape (K = 8) it reached
+// 90 % of the MUFU pipe, this kernel 94 %.
 // KU > 0: every variable has exactly KU components (unrolled, log2 shared by pairs of variables);
 // KU = 0: per-variable counts (runtime loop, one log2 per variable).
 template <int KU>
@@ -246,7 +246,8 @@ __device__ __forceinline__ void cp_async_wait_px() { asm volatile("cp.async.wait
 constexpr int PX_WARPS = 16;
 // shared memory: coefficients of the 32-state slice [C][KS][32] x {s, m, c, -}, the categorical table
 // [D][Vmax+1][32], then per warp two stages of observations [C][PG] x float4 and symbols [D][PG] x uint32
-template <int KU>
+// BIGP: more than 64 staging pieces per group (many variables x many lane groups of few states): piece offsets on the fly
+template <int KU, bool BIGP = false>
 __global__ void __launch_bounds__(PX_WARPS * 32, 2) k_emission_px(EmitArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
@@ -302,7 +303,6 @@ __global__ void __launch_bounds__(PX_WARPS * 32, 2) k_emission_px(EmitArgs a) {
     const int pb = g * group;
     float4 *xd = xs + st * xstage;
     uint32_t *vd = vs + st * vstage;
-    const int npmax = npx > npv ? npx : npv;
     if (a.vec && pb + group <= a.np) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -310,14 +310,16 @@ __global__ void __launch_bounds__(PX_WARPS * 32, 2) k_emission_px(EmitArgs a) {
         if (i < npx) cp_async16(xd + i, cont0 + poff[h] + pb);
         if (i < npv) cp_async4(vd + i, disc0 + poff[h] + pb);
       }
-      for (int i = lane + 64; i < npmax; i += 32) {            // (many variables x many lane groups: offsets on the fly)
-        const int64_t off = piece_off(i) + pb;
-        if (i < npx) cp_async16(xd + i, cont0 + off);
-        if (i < npv) cp_async4(vd + i, disc0 + off);
+      if (BIGP) {
+        for (int i = lane + 64; i < (npx > npv ? npx : npv); i += 32) {
+          const int64_t off = piece_off(i) + pb;
+          if (i < npx) cp_async16(xd + i, cont0 + off);
+          if (i < npv) cp_async4(vd + i, disc0 + off);
+        }
       }
     } else {
 #pragma unroll 1
-      for (int i = lane; i < npmax; i += 32) {
+      for (int i = lane; i < (BIGP ? (npx > npv ? npx : npv) : 64); i += 32) {
         const int q = pb + (i % PG) * EPU;
         const int64_t off = piece_off(i) + pb;
         if (i < npx) {
@@ -814,12 +816,13 @@ static int emit_px_ku(const dnbc_ctx *c) {                   // the common compo
 bool mixture_emission_fast(const dnbc_ctx *c) {
   const Dims &d = c->dm;
   const int KU = emit_px_ku(c);
-  return d.Kmax <= 8 && d.C <= 64 && emit_px_smem(d, KU > 0 ? KU : d.Kmax, 32 / lane_group(d, false)) <= 200 * 1024;
+  (void)KU;                                                  // (Kmax slots are the upper bound of both instantiations)
+  return d.Kmax <= 8 && d.C <= 64 && emit_px_smem(d, d.Kmax, 32 / lane_group(d, false)) <= 200 * 1024;
 }
-template <int KU>
+template <int KU, bool BIGP = false>
 static void launch_emit_px_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem) {
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_px<KU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_emission_px<KU><<<grid, PX_WARPS * 32, smem, c->stream>>>(a);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_px<KU, BIGP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_emission_px<KU, BIGP><<<grid, PX_WARPS * 32, smem, c->stream>>>(a);
 }
 
 void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
@@ -832,7 +835,10 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
   // the next group and store the same values.
   const int LG = lane_group(d, false);
   EmitArgs a{d, c->tables(), c->data(), p0, (int)np, out, LG, vec};
-  const int KU = emit_px_ku(c);
+  // (more than 64 staging pieces per group -- e.g. 16 lane groups of 2 states x 5 variables -- take the instantiation
+  // with per-variable component counts, which computes piece offsets on the fly)
+  const bool bigp = d.C * (32 / LG) > 64 || d.D * (32 / LG) > 64;
+  const int KU = bigp ? 0 : emit_px_ku(c);
   const size_t smem_px = emit_px_smem(d, KU > 0 ? KU : d.Kmax, 32 / LG);
   const int gy = (d.N + 31) / 32;                            // slices of 32 states that hold a real state
   int per_sm = (int)((200 * 1024) / (smem_px + 1024));
@@ -852,7 +858,10 @@ void launch_mixture_emission(dnbc_ctx *c, int64_t p0, int64_t np, float *out) {
     case 6: launch_emit_px_t<6>(c, a, grid, smem_px); break;
     case 7: launch_emit_px_t<7>(c, a, grid, smem_px); break;
     case 8: launch_emit_px_t<8>(c, a, grid, smem_px); break;
-    default: launch_emit_px_t<0>(c, a, grid, smem_px); break;
+    default:
+      if (bigp) launch_emit_px_t<0, true>(c, a, grid, smem_px);
+      else launch_emit_px_t<0>(c, a, grid, smem_px);
+      break;
   }
 }
 
