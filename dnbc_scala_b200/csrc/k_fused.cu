@@ -23,7 +23,7 @@
 // the shared-memory arrays, read back as group-wide broadcasts: no shuffles, no reductions trees -- every
 // lane sums the row it has to read anyway.  The transition matrix lives in registers (column j for the
 // forward pass, row i for the backward pass).  Phases E and S run variable by variable with that
-// variable's mixture coefficients in registers; they are MUFU-bound like k_emission_pk / k_stats2.
+// variable's mixture coefficients in registers; they are MUFU-bound like k_emission_px / k_stats2.
 // fp32 accumulators (per sequence in registers, per warp in shared memory) are folded into the fp64
 // statistics every ~4096 timesteps.  No reference counterpart; checked against the fp64
 // oracle like the general pipeline, whose results it reproduces to fp32 rounding.

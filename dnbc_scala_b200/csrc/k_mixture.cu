@@ -75,7 +75,7 @@ constexpr float EMIT_SHIFT = 30.f;       // log2 scale of the staged mixture con
 // ---------------------------------------------------------------------------------
 // K1 emission, packed over POINTS (k_emission_px)
 // ---------------------------------------------------------------------------------
-// The same sums as k_emission_pk, but the two halves of a packed instruction are two consecutive points of ONE
+// The same sums as the component-packed kernel it replaced (k_emission_pk), but the two halves of a packed instruction are two consecutive points of ONE
 // mixture component instead of two components at one point.  A component's coefficients then enter the FFMA2 as
 // scalar broadcast operands (SASS: FFMA2 R, R.F32x2, R.F32, R.F32), so
 //   * an odd component count costs nothing (K = 3 is three component steps, not a pair plus a scalar tail with
