@@ -24,7 +24,7 @@ def flagged_or_equal(path, opath, tie, otie, off, backtrace):
 
 def one(case, rng, large=False):
     N = int(rng.choice([256, 300, 512] if large else
-                       [1, 2, 3, 5, 6, 7, 9, 10, 12, 16, 17, 31, 32, 33, 48, 63, 64, 65, 96, 128, 130, 200, 256, 300]))
+                       [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 17, 31, 32, 33, 48, 63, 64, 65, 96, 128, 130, 200, 256, 300]))
     D = int(rng.integers(0, 4))
     C = int(rng.integers(0, 4)) if D else int(rng.integers(1, 4))
     V = [int(rng.integers(2, 12)) for _ in range(D)]
@@ -51,6 +51,8 @@ def one(case, rng, large=False):
     # (every other case keeps the register-resident recursions on their four-sequences-per-group variant)
     with ctx_for(nat, q) as ctx:
         ctx.set_option(nat.OPT_FB2_INTERLEAVE, case % 2)
+        ctx.set_option(nat.OPT_FB_SEQ_LANES, 1 if case % 3 == 0 else 0)    # every third case: lane-per-sequence recursions
+        ctx.set_option(nat.OPT_FUSED_ESTEP, 2 if case % 3 == 0 else 0)     # (they sit behind the general pipeline)
         upload(ctx, data, labels=False)
         ctx.em_estep()
         got = ctx.em_get_stats()

@@ -1,5 +1,7 @@
 #!/bin/bash
-# round-2 GPU call E9: GPU suite after the removal of the component-packed emission kernel; timings
+# round-2 GPU call E10: randomised parity sweep over the session's kernels (points-packed emission, lane-per-sequence
+# recursions on every third case, statistics sweep without the software pipeline, static rings of k_fb2)
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -k "not two_gpus" > gpurun_out/e9_pytest.log 2>&1; tail -4 gpurun_out/e9_pytest.log
-for w in "scaleout 32000 3" "largeN 12500 3" "gmm100k 100000 3" "readme 1000 3" "robot 200 3"; do python tools/kbench.py $w 2>> gpurun_out/e9_err.log | cut -c1-300; done
+FUZZ_LONG=1 timeout 1200 python tests/fuzz_parity.py 700 20261020 > gpurun_out/e10_fuzz.log 2>&1; echo "fuzz rc=$?"; tail -4 gpurun_out/e10_fuzz.log | cut -c1-300
+timeout 600 python tests/fuzz_parity.py 12 77 large > gpurun_out/e10_fuzz_large.log 2>&1; echo "fuzz large rc=$?"; tail -2 gpurun_out/e10_fuzz_large.log | cut -c1-300
+timeout 600 python tests/fuzz_parity.py 150 99 mle > gpurun_out/e10_fuzz_mle.log 2>&1; echo "fuzz mle rc=$?"; tail -2 gpurun_out/e10_fuzz_mle.log | cut -c1-300
