@@ -107,6 +107,8 @@ __device__ __forceinline__ u64 lg2_2(u64 a) {
 // (profiles/r02e_emission_elimination.jsonl).  Re-evaluating all four points of a flagged lane at once, packed, is
 // slower (9.36 vs 8.77 ms: usually one of the four is flagged); what helps is fewer and shorter evaluations --
 // emit_var_px's loop over each lane's next flagged point, and unrolled component loops here: 8.78 -> 8.06 ms.
+// Deferring the flagged (variable, point) pairs of a lane to after its last variable, so that lanes flagged at
+// different variables share their evaluations, changes nothing (7.97 vs 7.96 ms; +1.5 % at N = 10): not kept.
 __device__ __noinline__ float emit_px_slow(const float4 *ps, int kc, float x, float shift) {
   float mx = -INFINITY;
   for (int k = 0; k < kc; ++k) {

@@ -1,7 +1,15 @@
 #!/bin/bash
-# round-2 GPU call E10: randomised parity sweep over the session's kernels (points-packed emission, lane-per-sequence
-# recursions on every third case, statistics sweep without the software pipeline, static rings of k_fb2)
+# round-2 GPU call E11: deferred exponent-shifted re-evaluations in k_emission_px against the previous commit
 mkdir -p gpurun_out
-FUZZ_LONG=1 timeout 1200 python tests/fuzz_parity.py 700 20261020 > gpurun_out/e10_fuzz.log 2>&1; echo "fuzz rc=$?"; tail -4 gpurun_out/e10_fuzz.log | cut -c1-300
-timeout 600 python tests/fuzz_parity.py 12 77 large > gpurun_out/e10_fuzz_large.log 2>&1; echo "fuzz large rc=$?"; tail -2 gpurun_out/e10_fuzz_large.log | cut -c1-300
-timeout 600 python tests/fuzz_parity.py 150 99 mle > gpurun_out/e10_fuzz_mle.log 2>&1; echo "fuzz mle rc=$?"; tail -2 gpurun_out/e10_fuzz_mle.log | cut -c1-300
+rm -f gpurun_out/e11_kbench.jsonl
+timeout 900 python -m pytest tests -m gpu -q -x -k "emission or outlier or config5 or n512 or randomised or fused_and_general" > gpurun_out/e11_pytest.log 2>&1; tail -3 gpurun_out/e11_pytest.log
+for w in "largeN 12500 3" "gmm100k 100000 3 2" "readme 16000 3 2"; do
+for lib in "" build/libdnbc_pxprev.so "" build/libdnbc_pxprev.so; do
+  DNBC_B200_LIB=$lib python tools/kbench.py $w >> gpurun_out/e11_kbench.jsonl 2>> gpurun_out/e11_err.log
+done
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/e11_kbench.jsonl'):
+    d = json.loads(l); print(d['lib'], d['workload'], d['ms_per_iter']['emission'], d['ll'])
+PY
