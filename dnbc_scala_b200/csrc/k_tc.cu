@@ -1,5 +1,5 @@
-// k_tc.cu -- K6: forward / backward recursions for large state spaces (Npad = 256 or 512) on
-// the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+// k_tc.cu -- K6: forward / backward recursions for large state spaces (65 .. 512 states, padded to a
+// multiple of 64: NP = 128, 192, ... 512) on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
 //
 // No reference counterpart (the reference has no forward-backward); parity is
 // against the fp64 oracle (oracle/dnbc_oracle.c fb_one), same outputs as k_fb2.cu.
@@ -50,78 +50,65 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI) : "memory"); }
 
-// split 32 fp32 values (row r, columns c0 .. c0+31 of X) into bf16 hi / lo and store them into the staging
-// copy, which is laid out as the shared-memory images of the K-block tiles: [kb][hi | lo][128 x 64 swizzled]
-__device__ __forceinline__ void store_split(const float (&x)[32], unsigned char *xt, int r, int c0) {
-  uint32_t h[16], l[16];
+// the initial distribution for columns j0 .. j0+31 (the same 32 values in every lane: broadcast loads)
+__device__ __forceinline__ void load_pi32(const float *g, int j0, int N, float (&v)[32]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
-  unsigned char *tile = xt + (size_t)(c0 >> 6) * (2 * A_TILE);
-  const int cb = (c0 & 63) >> 3;                            // first 16-byte chunk of the row: 0 or 4
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t o = sw128(r, cb + i);
-    *(uint4 *)(tile + o) = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-    *(uint4 *)(tile + A_TILE + o) = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
-  }
-}
-
-// 32 consecutive floats of a row: vector path when the row pitch keeps 16-byte alignment
-__device__ __forceinline__ void load32(const float *g, int j0, int N, bool vec, bool on, float fill, float (&v)[32]) {
-  if (on && vec) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 q = __ldg((const float4 *)(g + j0) + i);
-      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (on && j0 + i < N) ? g[j0 + i] : fill;
-  }
-}
-__device__ __forceinline__ void store32(float *g, int j0, int N, bool vec, const float (&v)[32]) {
-  if (vec) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ((float4 *)(g + j0))[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (j0 + i < N) g[j0 + i] = v[i];
-  }
+  for (int i = 0; i < 32; ++i) v[i] = j0 + i < N ? __ldg(g + j0 + i) : 0.f;
 }
 
 // ---- coalesced global traffic for the epilogue ----------------------------------------------------
 // An epilogue thread owns one sequence row (its TMEM lane), but a warp-wide access in which every lane
 // touches a different row costs one LSU cycle per row.  32 x 32 fp32 chunks therefore go through a
-// warp-private 4 KB shared-memory tile (16-byte slots XOR-swizzled by the row, conflict-free both ways):
-// global accesses are made with lane = (row it*4 + lane/8, 16-byte slot lane%8), i.e. 4 rows x 128
-// contiguous bytes per instruction, and the tile is read / written by row on the other side.
+// warp-private 4 KB shared-memory tile (16-byte slots XOR-swizzled by the row, conflict-free both ways);
+// the tile is read / written by row on the thread's side, and global accesses are made
+//   V4 (N a multiple of 32: rows are whole float4's, a chunk is all states or all padding):
+//       lane = (row it*4 + lane/8, 16-byte slot lane%8), 4 rows x 128 contiguous bytes per instruction;
+//   otherwise (any N: the row pitch is only 4-byte aligned):
+//       lane = column, one row of 32 consecutive floats per instruction, columns past N masked off.
+// The first version of the any-N epilogue let every thread walk its own row (32 rows per warp access): N = 200
+// ran at 74 ms per 5e6 points where N = 256 took 12.
 constexpr int TB_BYTES = 32 * 128;
+constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ uint32_t tb_off(int r, int c4) { return (uint32_t)(r * 128 + ((c4 ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t tb_off1(int r, int c) { return tb_off(r, c >> 2) + (uint32_t)(c & 3) * 4u; }
 
-// issue the loads of columns col .. col+31 of the warp's 32 rows (pp = point index of row it*4 + lane/8).
+// issue the loads of columns col .. col+31 of the warp's 32 rows into q (p = this lane's row's point index;
+// pp = point index of row it*4 + lane/8, used by the V4 form only).
 // LAST: this is the last use of the lines (evict-first), so that the per-step streams (emissions, alpha,
 // gamma, u: ~150 MB per step over the chip) do not push the staging tiles and the transition matrix out of L2.
-template <bool LAST>
-__device__ __forceinline__ void chunk_ldg(const float *base, const int (&pp)[8], unsigned mask, int N, int col, int lane,
-                                          float fill, float4 (&q)[8]) {
+template <bool LAST, bool V4>
+__device__ __forceinline__ void chunk_ldg(const float *base, const int (&pp)[8], int p, unsigned mask, int N, int col, int lane,
+                                          float fill, float (&q)[32]) {
+  if (V4) {
+    if (col >= N) mask = 0u;                                 // a chunk of padded columns
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + (lane >> 3);
-    const float4 *src = (const float4 *)(base + (int64_t)pp[it] * N + col) + (lane & 7);
-    q[it] = ((mask >> rr) & 1u) ? (LAST ? __ldcs(src) : __ldg(src)) : make_float4(fill, fill, fill, fill);
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const float4 *src = (const float4 *)(base + (int64_t)pp[it] * N + col) + (lane & 7);
+      const float4 v = ((mask >> rr) & 1u) ? (LAST ? __ldcs(src) : __ldg(src)) : make_float4(fill, fill, fill, fill);
+      q[4 * it] = v.x; q[4 * it + 1] = v.y; q[4 * it + 2] = v.z; q[4 * it + 3] = v.w;
+    }
+  } else {
+    const bool con = col + lane < N;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+      const int pr = __shfl_sync(FULL, p, it);
+      const float *src = base + (int64_t)pr * N + col + lane;
+      q[it] = (con && ((mask >> it) & 1u)) ? (LAST ? __ldcs(src) : __ldg(src)) : fill;
+    }
   }
 }
 // ... and hand every thread the 32 values of its own row
-__device__ __forceinline__ void chunk_to_rows(unsigned char *tb, int lane, const float4 (&q)[8], float (&v)[32]) {
+template <bool V4>
+__device__ __forceinline__ void chunk_to_rows(unsigned char *tb, int lane, const float (&q)[32], float (&v)[32]) {
+  if (V4) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) *(float4 *)(tb + tb_off(it * 4 + (lane >> 3), lane & 7)) = q[it];
+    for (int it = 0; it < 8; ++it)
+      *(float4 *)(tb + tb_off(it * 4 + (lane >> 3), lane & 7)) = make_float4(q[4 * it], q[4 * it + 1], q[4 * it + 2], q[4 * it + 3]);
+  } else {
+#pragma unroll
+    for (int it = 0; it < 32; ++it) *(float *)(tb + tb_off1(it, lane)) = q[it];
+  }
   __syncwarp();
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4) {
@@ -136,14 +123,44 @@ __device__ __forceinline__ void rows_to_tb(unsigned char *tb, int lane, const fl
     *(float4 *)(tb + tb_off(lane, c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
   __syncwarp();
 }
-// tile -> rows (pp[it] + drow) of a row-major fp32 array, columns col .. col+31, rows selected by mask
-__device__ __forceinline__ void tb_store_f32(const unsigned char *tb, float *base, const int (&pp)[8], unsigned mask, int N,
+// tile -> rows (point + drow) of a row-major fp32 array, columns col .. col+31, rows selected by mask
+template <bool V4>
+__device__ __forceinline__ void tb_store_f32(const unsigned char *tb, float *base, const int (&pp)[8], int p, unsigned mask, int N,
                                              int col, int lane, int drow) {
+  if (V4) {
+    if (col >= N) return;                                    // padded columns are never written
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + (lane >> 3);
-    if ((mask >> rr) & 1u)                                   // streaming store: the consumers are later kernels
-      __stcs((float4 *)(base + (int64_t)(pp[it] + drow) * N + col) + (lane & 7), *(const float4 *)(tb + tb_off(rr, lane & 7)));
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      if ((mask >> rr) & 1u)                                 // streaming store: the consumers are later kernels
+        __stcs((float4 *)(base + (int64_t)(pp[it] + drow) * N + col) + (lane & 7), *(const float4 *)(tb + tb_off(rr, lane & 7)));
+    }
+  } else {
+    const bool con = col + lane < N;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+      const int pr = __shfl_sync(FULL, p, it);
+      if (con && ((mask >> it) & 1u)) __stcs(base + (int64_t)(pr + drow) * N + col + lane, *(const float *)(tb + tb_off1(it, lane)));
+    }
+  }
+}
+// zeros into columns col .. col+31 of the rows selected by mask
+template <bool V4>
+__device__ __forceinline__ void zero_rows(float *base, const int (&pp)[8], int p, unsigned mask, int N, int col, int lane) {
+  if (V4) {
+    if (col >= N) return;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      if ((mask >> rr) & 1u) *((float4 *)(base + (int64_t)pp[it] * N + col) + (lane & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    const bool con = col + lane < N;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+      const int pr = __shfl_sync(FULL, p, it);
+      if (con && ((mask >> it) & 1u)) base[(int64_t)pr * N + col + lane] = 0.f;
+    }
   }
 }
 // tile -> bf16 hi / lo split into the staging tile images (rows row0 .. row0+31, columns c0 .. c0+31 of X):
@@ -172,7 +189,7 @@ __device__ __forceinline__ void tb_store_split(const unsigned char *tb, unsigned
 }
 
 struct TcArgs {
-  int N, NP;                    // states, padded states (256 or 512)
+  int N, NP;                    // states, states padded to a multiple of 64 (128 .. 512)
   const int64_t *off;
   int64_t s0, s1, p0;
   const float *E;               // [np][N]
@@ -185,36 +202,45 @@ struct TcArgs {
   unsigned char *Xt;            // [grid] staging of the next step's operand X as tile images: [kb][hi | lo][128 x 64]
 };
 
-// Producer (one thread): stream the K-block tiles of X and B for one step into the ring.
+// Producer (one thread): stream the K-block tiles of X and B for one step into the ring.  The accumulator is
+// formed in column blocks of up to 256 (UMMA N); the last block of a padded state count that is not a multiple of
+// 256 has 64, 128 or 192 columns, and only those rows of the B tile images are fetched (the first `rows` rows of
+// a 128-byte-swizzled K-major tile are its first rows * 128 bytes).
 __device__ void tc_produce(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty, uint32_t (&uses)[2],
                            const unsigned char *xt) {
-  const int nkb = a.NP / TC_KB, nnh = a.NP / TC_NH;
+  const int nkb = a.NP / TC_KB, nnh = (a.NP + TC_NH - 1) / TC_NH;
   int it = 0;
   for (int nh = 0; nh < nnh; ++nh) {
+    const int rows = a.NP - nh * TC_NH < TC_NH ? a.NP - nh * TC_NH : TC_NH;
+    const uint32_t bbytes = (uint32_t)rows * 128u;           // hi (and lo) bytes of this block's B tile
     for (int kb = 0; kb < nkb; ++kb, ++it) {
       const int s = it & 1;
       const uint32_t st = smem_base + s * STAGE_BYTES, full = bar_full + 8 * s;
       // the stage is free once the MMAs that read its previous contents have completed
       if (uses[s] > 0) mbar_wait(bar_empty + 8 * s, (uses[s] - 1) & 1);
-      mbar_expect_tx(full, STAGE_BYTES);
+      mbar_expect_tx(full, 2 * A_TILE + 2 * bbytes);
       const unsigned char *xs = xt + (size_t)kb * (2 * A_TILE);
       const unsigned char *bs = a.Bt + ((size_t)nh * nkb + kb) * (2 * B_TILE);
 #pragma unroll
       for (uint32_t o = 0; o < 2 * A_TILE; o += BULK) bulk_g2s(st + o, xs + o, BULK, full);
-#pragma unroll
-      for (uint32_t o = 0; o < 2 * B_TILE; o += BULK) bulk_g2s(st + 2 * A_TILE + o, bs + o, BULK, full);
+      for (uint32_t o = 0; o < bbytes; o += BULK) {
+        const uint32_t n = bbytes - o < BULK ? bbytes - o : BULK;
+        bulk_g2s(st + 2 * A_TILE + o, bs + o, n, full);
+        bulk_g2s(st + 2 * A_TILE + B_TILE + o, bs + B_TILE + o, n, full);
+      }
       uses[s] += 1;
     }
   }
 }
 
-// MMA issuer (one thread): D[128][NP] (TMEM) = X[128][NP] * B^T, 256 accumulator columns at a time
+// MMA issuer (one thread): D[128][NP] (TMEM) = X[128][NP] * B^T, up to 256 accumulator columns at a time
 __device__ void tc_mma(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_done,
                        uint32_t tmem, uint32_t (&uses)[2]) {
-  const int nkb = a.NP / TC_KB, nnh = a.NP / TC_NH;
-  const uint32_t idesc = umma_idesc(TC_M, TC_NH);
+  const int nkb = a.NP / TC_KB, nnh = (a.NP + TC_NH - 1) / TC_NH;
   int it = 0;
   for (int nh = 0; nh < nnh; ++nh) {
+    const int rows = a.NP - nh * TC_NH < TC_NH ? a.NP - nh * TC_NH : TC_NH;
+    const uint32_t idesc = umma_idesc(TC_M, rows);
     for (int kb = 0; kb < nkb; ++kb, ++it) {
       const int s = it & 1;
       const uint32_t st = smem_base + s * STAGE_BYTES;
@@ -231,7 +257,7 @@ __device__ void tc_mma(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, u
         umma_bf16(d, dAl + ko, dBh + ko, idesc, 1u);
       }
       umma_commit(bar_empty + 8 * s);
-      if (kb == nkb - 1) umma_commit(bar_done + 8 * nh);   // this half of the accumulator is complete
+      if (kb == nkb - 1) umma_commit(bar_done + 8 * nh);   // this block of the accumulator is complete
       uses[s] += 1;
     }
   }
@@ -248,7 +274,7 @@ __device__ void tc_mma(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, u
 #define TCT_LAP(i)
 #endif
 
-template <int DIR>   // 0 = forward, 1 = backward
+template <int DIR, bool V4>   // DIR: 0 = forward, 1 = backward; V4: N is a multiple of 32 (float4 form of the epilogue traffic)
 __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
   TCT_DECL;
   extern __shared__ unsigned char smraw[];
@@ -261,11 +287,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const bool epi = w < TC_EPI / 32;
   const int row = (w & 3) * 32 + lane, half = (w >> 2) & 1;  // TMEM lane quadrant = warp % 4
-  const int ncol = NP / 2, col0 = half * ncol;               // this thread's column range
-  const bool vec = (N % 4) == 0 && N == NP;                  // rows are whole float4's and no padded columns
+  const int ncol = NP / 2, col0 = half * ncol;               // this thread's column range (whole 32-column chunks)
   const uint32_t smem_base = (smem_u32(smraw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[2]), bar_done = smem_u32(&bars[4]);
-  const uint32_t my_done = bar_done + 8 * (col0 / TC_NH);    // the accumulator half this thread's columns are in
+  const uint32_t my_done = bar_done + 8 * ((col0 + ncol - 1) / TC_NH);   // the last accumulator block this thread's columns are in
   unsigned char *tb = smraw + (smem_base - smem_u32(smraw)) + 2 * STAGE_BYTES + (w & 7) * TB_BYTES;   // this warp's transpose tile
   const int row0 = (w & 3) * 32;
   if (tid == 0) {
@@ -312,70 +337,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
       const int t = DIR == 0 ? k : T - 1 - k;
       const bool live = DIR == 0 ? (k < T) : (t >= 0);
       const int64_t p = pt + (live ? t : 0);
-      const float *Erow = a.E + p * N;
+      const int pi32 = (int)p;
       const float mx = live ? a.mrow[p] : 0.f;
       const float mxs = mx == -INFINITY ? 0.f : mx;
+      const unsigned lmask = __ballot_sync(FULL, live);
+      int pp[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) pp[it] = V4 ? __shfl_sync(FULL, pi32, it * 4 + (lane >> 3)) : 0;
       if (DIR == 0) {
-        // ---- v = d * exp(E - m); c = sum v; alpha = v / c ----
+        // ---- v = d * exp(E - m); c = sum v; alpha = v / c ----   (emission chunks are fetched one chunk ahead)
         float sum = 0.f;
-        if (vec) {
-          // coalesced path (tb_* helpers): emission chunks are fetched one chunk ahead
-          const unsigned lmask = __ballot_sync(0xffffffffu, live);
-          int pp[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
-          float4 en4[8];
-          chunk_ldg<true>(a.E, pp, lmask, N, col0, lane, -INFINITY, en4);
-          if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
-          TCT_LAP(0);
-          for (int ch = 0; ch < ncol / 32; ++ch) {
-            const int c0 = col0 + ch * 32;
-            float d[32], e[32];
-            chunk_to_rows(tb, lane, en4, e);
-            if (ch + 1 < ncol / 32) chunk_ldg<true>(a.E, pp, lmask, N, c0 + 32, lane, -INFINITY, en4);
-            if (k > 0) tmem_ld32(trow + c0, d);
-            else load32(a.pi, c0, N, false, true, 0.f, d);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              d[i] *= ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E);
-              sum += d[i];
-            }
-            tmem_st32(trow + c0, d);
-          }
-          rsum[row][half] = sum;
-          TCT_LAP(1);
-          epi_sync();
-          TCT_LAP(2);
-          const float c = rsum[row][0] + rsum[row][1];
-          const float inv = live ? 1.0f / c : 0.f;
-          for (int ch = 0; ch < ncol / 32; ++ch) {
-            const int c0 = col0 + ch * 32;
-            float d[32];
-            tmem_ld32(trow + c0, d);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) d[i] *= inv;
-            rows_to_tb(tb, lane, d);
-            tb_store_f32(tb, a.AL, pp, lmask, N, c0, lane, 0);
-            tb_store_split(tb, xt, row0, c0, lane);
-            __syncwarp();
-          }
-          if (live && half == 0) {
-            a.cs[p] = c;
-            ll += (double)logf(c) + (double)mxs;
-          }
-        } else {
-        float e[32], en[32];
-        load32(Erow, col0, N, vec, live, -INFINITY, en);           // emission rows are fetched one chunk ahead
+        float en[32];
+        chunk_ldg<true, V4>(a.E, pp, pi32, lmask, N, col0, lane, -INFINITY, en);
         if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
         TCT_LAP(0);
         for (int ch = 0; ch < ncol / 32; ++ch) {
           const int c0 = col0 + ch * 32;
-          float d[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) e[i] = en[i];
-          if (ch + 1 < ncol / 32) load32(Erow, c0 + 32, N, vec, live, -INFINITY, en);
+          float d[32], e[32];
+          chunk_to_rows<V4>(tb, lane, en, e);
+          if (ch + 1 < ncol / 32) chunk_ldg<true, V4>(a.E, pp, pi32, lmask, N, c0 + 32, lane, -INFINITY, en);
           if (k > 0) tmem_ld32(trow + c0, d);
-          else load32(a.pi, c0, N, false, true, 0.f, d);
+          else load_pi32(a.pi, c0, N, d);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             d[i] *= ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E);
@@ -395,161 +377,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           tmem_ld32(trow + c0, d);
 #pragma unroll
           for (int i = 0; i < 32; ++i) d[i] *= inv;
-          if (live) store32(a.AL + p * N, c0, N, vec, d);
-          store_split(d, xt, row, c0);
+          rows_to_tb(tb, lane, d);
+          tb_store_f32<V4>(tb, a.AL, pp, pi32, lmask, N, c0, lane, 0);
+          tb_store_split(tb, xt, row0, c0, lane);
+          __syncwarp();
         }
         if (live && half == 0) {
           a.cs[p] = c;
           ll += (double)logf(c) + (double)mxs;
         }
-        }
       } else {
         // ---- beta_t in TMEM (1 on the last step); gamma = alpha * beta; next u = exp(E_t - m_t) beta / c_t ----
         const float ic = live ? 1.0f / a.cs[p] : 0.f;
-        if (vec) {
-          // coalesced path (tb_* helpers)
-          const unsigned lmask = __ballot_sync(0xffffffffu, live);
-          const unsigned tpos = __ballot_sync(0xffffffffu, live && t > 0);
-          int pp[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) pp[it] = __shfl_sync(0xffffffffu, (int)p, it * 4 + (lane >> 3));
-          float4 qa[8], qe[8];
-          chunk_ldg<false>(a.AL, pp, lmask, N, col0, lane, 0.f, qa);
-          // (no L2 prefetch of the step's rows: ~190 MB stream through the 126 MB L2 per step, so lines fetched a
-          // product phase ahead were evicted again before their use -- measured 97 -> 94 ms without it)
-          if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
-          TCT_LAP(0);
-          // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
-          // ~1e-5 per step, so beta^_t is rescaled to make it 1 at every step (as k_fb2 / k_fb3 do)
-          float sdot = 0.f;
-          for (int ch = 0; ch < ncol / 32; ++ch) {
-            const int c0 = col0 + ch * 32;
-            float d[32], al[32];
-            chunk_to_rows(tb, lane, qa, al);
-            if (ch + 1 < ncol / 32) chunk_ldg<false>(a.AL, pp, lmask, N, c0 + 32, lane, 0.f, qa);
-            if (k > 0) tmem_ld32(trow + c0, d);
-            else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) d[i] = 1.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sdot = fmaf(al[i], d[i], sdot);
-          }
-          rsum[row][half] = sdot;
-          TCT_LAP(1);
-          epi_sync();
-          TCT_LAP(2);
-          sdot = rsum[row][0] + rsum[row][1];
-          const float fix = (live && sdot > 0.f) ? 1.0f / sdot : 1.f;
-          for (int ch = 0; ch < ncol / 32; ++ch) {
-            const int c0 = col0 + ch * 32;
-            float d[32], e[32], al[32];
-            // (both rows were pulled into L2 at the top of the step; the TMEM load overlaps the fetch)
-            chunk_ldg<true>(a.AL, pp, lmask, N, c0, lane, 0.f, qa);
-            chunk_ldg<true>(a.E, pp, lmask, N, c0, lane, -INFINITY, qe);
-            if (k > 0) tmem_ld32(trow + c0, d);
-            else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) d[i] = 1.f;
-            }
-            chunk_to_rows(tb, lane, qa, al);
-            chunk_to_rows(tb, lane, qe, e);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              d[i] *= fix;
-              al[i] *= d[i];                                                   // gamma
-              e[i] = (live && t > 0) ? ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E) * d[i] * ic : 0.f;   // next u
-            }
-            rows_to_tb(tb, lane, al);
-            tb_store_f32(tb, a.GA, pp, lmask, N, c0, lane, 0);
-            __syncwarp();
-            const unsigned t0mask = __ballot_sync(0xffffffffu, live && t == 0);
-            if (t0mask) {
-              // pi-stat += gamma_0: the rows at their first step go through the tile once more and each lane adds up
-              // one state column, so a warp issues 32 atomics instead of 32 x 32 (148 batches hitting 512 addresses)
-              const bool mine = live && t == 0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) al[i] = mine ? al[i] : 0.f;
-              rows_to_tb(tb, lane, al);
-              float colsum = 0.f;
-#pragma unroll 8
-              for (int r = 0; r < 32; ++r) colsum += *(const float *)(tb + tb_off(r, lane >> 2) + (lane & 3) * 4);
-              if (colsum != 0.f) atomicAdd(a.stats + a.st_pi + c0 + lane, (double)colsum);
-              __syncwarp();
-            }
-            rows_to_tb(tb, lane, e);
-            tb_store_f32(tb, a.U, pp, tpos, N, c0, lane, -1);
-            if (k == 0) {                                                      // no transition out of the last step
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + (lane >> 3);
-                if ((lmask >> rr) & 1u) *((float4 *)(a.U + (int64_t)pp[it] * N + c0) + (lane & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
-            tb_store_split(tb, xt, row0, c0, lane);
-            __syncwarp();
-          }
-        } else {
+        const unsigned tpos = __ballot_sync(FULL, live && t > 0);
+        float qa[32], qe[32];
+        chunk_ldg<false, V4>(a.AL, pp, pi32, lmask, N, col0, lane, 0.f, qa);
+        // (no L2 prefetch of the step's rows: ~190 MB stream through the 126 MB L2 per step, so lines fetched a
+        // product phase ahead were evicted again before their use -- measured 97 -> 94 ms without it)
         if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
         TCT_LAP(0);
         // sum_j alpha^_t(j) beta^_t(j) is 1 in exact arithmetic; with split-bf16 products it drifts by
         // ~1e-5 per step, so beta^_t is rescaled to make it 1 at every step (as k_fb2 / k_fb3 do)
-        float fix = 1.f;
-        {
-          float s = 0.f;
-          for (int ch = 0; ch < ncol / 32; ++ch) {
-            const int c0 = col0 + ch * 32;
-            float d[32], al[32];
-            if (k > 0) tmem_ld32(trow + c0, d);
-            else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) d[i] = 1.f;
-            }
-            load32(a.AL + p * N, c0, N, vec, live, 0.f, al);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s = fmaf(al[i], d[i], s);
-          }
-          rsum[row][half] = s;
-          TCT_LAP(1);
-          epi_sync();
-          TCT_LAP(2);
-          s = rsum[row][0] + rsum[row][1];
-          fix = (live && s > 0.f) ? 1.0f / s : 1.f;
-        }
+        float sdot = 0.f;
         for (int ch = 0; ch < ncol / 32; ++ch) {
           const int c0 = col0 + ch * 32;
-          float d[32], e[32], al[32];
+          float d[32], al[32];
+          chunk_to_rows<V4>(tb, lane, qa, al);
+          if (ch + 1 < ncol / 32) chunk_ldg<false, V4>(a.AL, pp, pi32, lmask, N, c0 + 32, lane, 0.f, qa);
           if (k > 0) tmem_ld32(trow + c0, d);
           else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) d[i] = 1.f;
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) d[i] *= fix;
-          load32(Erow, c0, N, vec, live, -INFINITY, e);
-          load32(a.AL + p * N, c0, N, vec, live, 0.f, al);
+          for (int i = 0; i < 32; ++i) sdot = fmaf(al[i], d[i], sdot);
+        }
+        rsum[row][half] = sdot;
+        TCT_LAP(1);
+        epi_sync();
+        TCT_LAP(2);
+        sdot = rsum[row][0] + rsum[row][1];
+        const float fix = (live && sdot > 0.f) ? 1.0f / sdot : 1.f;
+        for (int ch = 0; ch < ncol / 32; ++ch) {
+          const int c0 = col0 + ch * 32;
+          float d[32], e[32], al[32];
+          // (both rows were pulled into L2 at the top of the step; the TMEM load overlaps the fetch)
+          chunk_ldg<true, V4>(a.AL, pp, pi32, lmask, N, c0, lane, 0.f, qa);
+          chunk_ldg<true, V4>(a.E, pp, pi32, lmask, N, c0, lane, -INFINITY, qe);
+          if (k > 0) tmem_ld32(trow + c0, d);
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = 1.f;
+          }
+          chunk_to_rows<V4>(tb, lane, qa, al);
+          chunk_to_rows<V4>(tb, lane, qe, e);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
+            d[i] *= fix;
             al[i] *= d[i];                                                   // gamma
             e[i] = (live && t > 0) ? ex2_approx((e[i] - mxs) * (float)DNBC_LOG2E) * d[i] * ic : 0.f;   // next u
           }
-          if (live) {
-            store32(a.GA + p * N, c0, N, vec, al);
-            if (t == 0) {
+          rows_to_tb(tb, lane, al);
+          tb_store_f32<V4>(tb, a.GA, pp, pi32, lmask, N, c0, lane, 0);
+          __syncwarp();
+          const unsigned t0mask = __ballot_sync(FULL, live && t == 0);
+          if (t0mask) {
+            // pi-stat += gamma_0: the rows at their first step go through the tile once more and each lane adds up
+            // one state column, so a warp issues 32 atomics instead of 32 x 32 (148 batches hitting 512 addresses)
+            const bool mine = live && t == 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c0 + i < N && al[i] != 0.f) atomicAdd(a.stats + a.st_pi + c0 + i, (double)al[i]);
-            }
-            if (t > 0) store32(a.U + (p - 1) * N, c0, N, vec, e);
-            if (k == 0) {                                                    // no transition out of the last step
-              float z[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) z[i] = 0.f;
-              store32(a.U + p * N, c0, N, vec, z);
-            }
+            for (int i = 0; i < 32; ++i) al[i] = mine ? al[i] : 0.f;
+            rows_to_tb(tb, lane, al);
+            float colsum = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) colsum += *(const float *)(tb + tb_off1(r, lane));
+            if (colsum != 0.f) atomicAdd(a.stats + a.st_pi + c0 + lane, (double)colsum);   // (padded columns sum to zero)
+            __syncwarp();
           }
-          store_split(e, xt, row, c0);
-        }
+          rows_to_tb(tb, lane, e);
+          tb_store_f32<V4>(tb, a.U, pp, pi32, tpos, N, c0, lane, -1);
+          if (k == 0) zero_rows<V4>(a.U, pp, pi32, lmask, N, c0, lane);         // no transition out of the last step
+          tb_store_split(tb, xt, row0, c0, lane);
+          __syncwarp();
         }
       }
       // the staging tiles are read by the bulk copies (async proxy) of the next step
@@ -608,24 +517,31 @@ __global__ void k_tc_tables(const double *__restrict__ A, int N, int NP, unsigne
 
 }  // namespace
 
-bool fb_tc_supported(const dnbc_ctx *c) {
-  return c->dm.Npad == 256 || c->dm.Npad == 512;
+// padded state count of the tensor-core recursion: a multiple of 64 (K blocks of 64 source states, two column halves
+// of whole 32-column chunks for the epilogue threads); 0 = not supported
+static int tc_np(const dnbc_ctx *c) {
+  const int N = c->dm.N;
+  return (N > 64 && N <= 512) ? (N + 63) / 64 * 64 : 0;
 }
+// bytes of one transition-matrix table: [column block of 256][K block][hi | lo][256 x 64]
+static size_t tc_table_bytes(int NP) { return (size_t)((NP + TC_NH - 1) / TC_NH) * (NP / TC_KB) * (2 * B_TILE); }
+
+bool fb_tc_supported(const dnbc_ctx *c) { return tc_np(c) != 0; }
 
 void launch_tc_tables(dnbc_ctx *c) {
-  const int NP = c->dm.Npad;
-  const size_t n = (size_t)NP * NP;
+  const int NP = tc_np(c);
+  const size_t tb = tc_table_bytes(NP);
   if (!c->tc_tab) {
-    if (cudaMalloc((void **)&c->tc_tab, 4 * n * sizeof(__nv_bfloat16)) != cudaSuccess) return;
+    if (cudaMalloc((void **)&c->tc_tab, 2 * tb) != cudaSuccess) return;
   }
   unsigned char *t = (unsigned char *)c->tc_tab;
   c->launches++;
-  k_tc_tables<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_A, c->dm.N, NP, t, t + 4 * n);
+  k_tc_tables<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_A, c->dm.N, NP, t, t + tb);
 }
 
 int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bool backward) {
-  const int NP = c->dm.Npad, N = c->dm.N;
-  const size_t n = (size_t)NP * NP;
+  const int NP = tc_np(c), N = c->dm.N;
+  const size_t tbytes = tc_table_bytes(NP);
   const int64_t batches = (s1 - s0 + TC_M - 1) / TC_M;
   int grid = (int)(batches < c->sm_count ? batches : c->sm_count);
   if (grid < 1) grid = 1;
@@ -642,16 +558,15 @@ int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bo
   const unsigned char *t = (const unsigned char *)c->tc_tab;
   StatsLayout sl = stats_layout(c->dm);
   TcArgs a{N, NP, c->d_off, s0, s1, p0, c->E, c->tc_mrow, c->AL, c->GA, c->U, c->cs, c->d_stats, sl.pi, c->t_pi,
-           backward ? t : t + 4 * n, (unsigned char *)c->tc_x};
+           backward ? t : t + tbytes, (unsigned char *)c->tc_x};
   const size_t smem = 2 * STAGE_BYTES + 1024 + (TC_EPI / 32) * TB_BYTES;   // ring + alignment slack + transpose tiles
   if (!backward) {
     c->launches++;
     k_rowmax<<<c->sm_count * 8, 256, 0, c->stream>>>(c->E, N, np, c->tc_mrow);
-    cudaFuncSetAttribute(k_fb_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fb_tc<0><<<grid, TC_THREADS, smem, c->stream>>>(a);
-  } else {
-    cudaFuncSetAttribute(k_fb_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fb_tc<1><<<grid, TC_THREADS, smem, c->stream>>>(a);
   }
+  // (the epilogue addresses points with 32-bit indices relative to the chunk: chunks stay below 2^31 points)
+  auto kf = backward ? (N % 32 == 0 ? k_fb_tc<1, true> : k_fb_tc<1, false>) : (N % 32 == 0 ? k_fb_tc<0, true> : k_fb_tc<0, false>);
+  cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kf<<<grid, TC_THREADS, smem, c->stream>>>(a);
   return DNBC_OK;
 }

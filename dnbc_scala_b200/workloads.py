@@ -59,6 +59,18 @@ WORKLOADS: Dict[str, Workload] = {
 }
 
 
+def by_name(name: str) -> Workload:
+    """A BASELINE configuration by name, or an ad-hoc shape for kernel timings:
+    "custom:N=128,D=5,C=5,K=3,T=200" (missing keys default to the largeN configuration's)."""
+    if not name.startswith("custom:"):
+        return WORKLOADS[name]
+    kv = dict(item.split("=") for item in name[7:].split(",") if item)
+    g = {k: int(v) for k, v in kv.items()}
+    N = g.get("N", 512)
+    return Workload(name, N=N, D=g.get("D", 5), C=g.get("C", 5), K=g.get("K", 3), T=g.get("T", 200), S=g.get("S", 100_000),
+                    transitions_per_state=g.get("tps", N), index=9)
+
+
 def true_params(wl: Workload) -> Dict[str, np.ndarray]:
     rng = np.random.default_rng(20260000 + wl.index)
     N, D, C, K, V = wl.N, wl.D, wl.C, wl.K, wl.V

@@ -1,6 +1,6 @@
 """Randomised parity sweep: random shapes / mixtures / ragged lengths, CUDA path vs the fp64 oracle.
 usage: python tests/fuzz_parity.py [cases] [seed] [mle|large]   (needs a B200; prints the first failure and exits 1)
-  mle   = supervised learner cases;  large = N in {256, 300, 512} with sequences of up to 400 steps"""
+  mle   = supervised learner cases;  large = N in {100, 192, 256, 300, 400, 512} with sequences of up to 400 steps"""
 import os
 import sys
 
@@ -23,8 +23,8 @@ def flagged_or_equal(path, opath, tie, otie, off, backtrace):
 
 
 def one(case, rng, large=False):
-    N = int(rng.choice([256, 300, 512] if large else
-                       [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 17, 31, 32, 33, 48, 63, 64, 65, 96, 128, 130, 200, 256, 300]))
+    N = int(rng.choice([100, 192, 256, 300, 400, 512] if large else
+                       [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 17, 31, 32, 33, 48, 63, 64, 65, 70, 96, 100, 128, 130, 160, 200, 256, 300, 320]))
     D = int(rng.integers(0, 4))
     C = int(rng.integers(0, 4)) if D else int(rng.integers(1, 4))
     V = [int(rng.integers(2, 12)) for _ in range(D)]

@@ -520,6 +520,35 @@ def test_bridge_clamped_em_reproduces_supervised_learner(oracle):
     np.testing.assert_allclose(p["var"], sup.var, rtol=1e-4)
 
 
+@pytest.mark.parametrize("N", [65, 96, 100, 128, 160, 192, 200, 288, 320, 352, 448, 500])
+def test_tensor_core_recursion_any_state_count(oracle, N):
+    """Every state count from 65 to 512 runs the tcgen05 recursions on a multiple-of-64 padding (k_tc.cu: K blocks of 64
+    source states, a last accumulator block of 64 / 128 / 192 columns, 32-column chunks of padding masked off in the
+    coalesced epilogue when N is a multiple of 32, row-strided epilogue otherwise): statistics, posteriors and two EM
+    iterations against the fp64 oracle over two 128-sequence batches of ragged lengths."""
+    m = random_model(oracle, N, [5], [2], 900 + N, transitions_per_state=min(N, 48))
+    rng = np.random.default_rng(901 + N)
+    lengths = [int(x) for x in rng.integers(1, 7, 134)] + [40, 0, 1]
+    data = sample(oracle, m, lengths, 902 + N)
+    q = perturb(oracle, m, 903 + N)
+    want = oracle.estep(q, data)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        g = ctx.em_posteriors()
+        ll = ctx.em_iterate(2)
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    for key in ("pi", "xi", "gamma", "cat"):
+        np.testing.assert_allclose(sg[key], sw[key], rtol=1e-4, atol=1e-4, err_msg=key)
+    np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
+    r = q.copy()
+    ll_want = oracle.em_iterate(r, data, 2)
+    np.testing.assert_allclose(ll, ll_want, rtol=TOL)
+
+
 def test_large_state_space_kernels(oracle):
     """N = 300 (padded to 512) exercises the CTA-per-sequence recursions."""
     m = random_model(oracle, 300, [6], [2], 81, transitions_per_state=40)

@@ -3,7 +3,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dnbc_scala_b200 import _native as nat, workloads
-wl = workloads.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "scaleout"]
+wl = workloads.by_name(sys.argv[1] if len(sys.argv) > 1 else "scaleout")
 seqs = int(sys.argv[2]) if len(sys.argv) > 2 else 32000
 truth = workloads.true_params(wl)
 ctx = nat.Context(wl.N, [wl.V] * wl.D, [wl.K] * wl.C, device=0)

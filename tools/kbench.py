@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dnbc_scala_b200 import _native as nat  # noqa: E402
 from dnbc_scala_b200 import workloads  # noqa: E402
 
-wl = workloads.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "scaleout"]
+wl = workloads.by_name(sys.argv[1] if len(sys.argv) > 1 else "scaleout")
 seqs = int(sys.argv[2]) if len(sys.argv) > 2 else 32000
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 truth = workloads.true_params(wl)
