@@ -57,34 +57,42 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo
 // tile row.  A thread's items are the same in every K block, so their coordinates are computed
 // once: `g` = element offset from the block's first point, `so` = swizzled byte offset in the tile.
 struct Item {
-  int g;
+  int g, k0;                    // k0 = first point of the chunk inside the K block
   uint32_t so;
   bool on;
 };
+// Items of states past N inside a partial tile load the tile's last real column again (lines their neighbours fetch
+// anyway) and store nothing: their rows of the operand tiles keep the zeros of the initial fill.  They used to walk
+// the guarded tail path -- an integer division and eight predicated loads per item and K block -- which is twice the
+// instructions of the plain path, so the warps WITHOUT work set the pace of every CTA with a partial tile: N = 320
+// took 7.7 ms per 2.5e6 points where N = 384 (nine full tiles) takes 4.2, with 5.97 GB of DRAM reads for 3.07 GB of
+// rows (ncu: the slower CTAs of a slab fall out of the L2 window of the faster ones).
 __device__ __forceinline__ Item make_item(int q, int rows, int valid, int N, int col0) {
   Item it;
   const int r = q % rows, c = q / rows;
-  it.on = q < rows * 8 && r < valid;
-  it.g = c * 8 * N + col0 + r;
+  it.on = r < valid;
+  it.g = c * 8 * N + col0 + (r < valid ? r : valid - 1);
+  it.k0 = c * 8;
   it.so = sw128(r, c);
   return it;
 }
 __device__ __forceinline__ void load_item(const Item &it, const float *__restrict__ blk, int N, int64_t left, float (&x)[8]) {
-  if (it.on && left >= XKB) {                                // whole block inside the slab
-    const float *g = blk + it.g;
+  const float *g = blk + it.g;
+  if (left >= XKB) {                                         // whole block inside the slab
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = __ldg(g + (int64_t)k * N);
   } else {
-    const int k0 = (it.g / N);                               // first point of the chunk (col0 + r < N)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (it.on && k0 + k < left) ? __ldg(blk + it.g + (int64_t)k * N) : 0.f;
+    for (int k = 0; k < 8; ++k) x[k] = it.k0 + k < left ? __ldg(g + (int64_t)k * N) : 0.f;
   }
 }
 __device__ __forceinline__ void store_item(const Item &it, uint32_t tile_hi, uint32_t tile_lo, const float (&x)[8]) {
   uint4 hi, lo;
   split8(x, hi, lo);
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_hi + it.so), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + it.so), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+  if (it.on) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_hi + it.so), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + it.so), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+  }
 }
 
 // NJ = UMMA N = to-states per tile (64 or 128); AM = rows of the A tile that exist in shared
