@@ -61,7 +61,7 @@ __device__ __forceinline__ void load_pi32(const float *g, int j0, int N, float (
 // touches a different row costs one LSU cycle per row.  32 x 32 fp32 chunks therefore go through a
 // warp-private 4 KB shared-memory tile (16-byte slots XOR-swizzled by the row, conflict-free both ways);
 // the tile is read / written by row on the thread's side, and global accesses are made
-//   V4 (N a multiple of 32: rows are whole float4's, a chunk is all states or all padding):
+//   V4 (N a multiple of 4: rows are whole, 16-byte aligned float4's; a slot is all states or all padding):
 //       lane = (row it*4 + lane/8, 16-byte slot lane%8), 4 rows x 128 contiguous bytes per instruction;
 //   otherwise (any N: the row pitch is only 4-byte aligned):
 //       lane = column, one row of 32 consecutive floats per instruction, columns past N masked off.
@@ -80,7 +80,7 @@ template <bool LAST, bool V4>
 __device__ __forceinline__ void chunk_ldg(const float *base, const int (&pp)[8], int p, unsigned mask, int N, int col, int lane,
                                           float fill, float (&q)[32]) {
   if (V4) {
-    if (col >= N) mask = 0u;                                 // a chunk of padded columns
+    if (col + (lane & 7) * 4 >= N) mask = 0u;                // this lane's float4 slot is padding
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + (lane >> 3);
@@ -128,7 +128,7 @@ template <bool V4>
 __device__ __forceinline__ void tb_store_f32(const unsigned char *tb, float *base, const int (&pp)[8], int p, unsigned mask, int N,
                                              int col, int lane, int drow) {
   if (V4) {
-    if (col >= N) return;                                    // padded columns are never written
+    if (col + (lane & 7) * 4 >= N) return;                   // padded columns are never written
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + (lane >> 3);
@@ -148,7 +148,7 @@ __device__ __forceinline__ void tb_store_f32(const unsigned char *tb, float *bas
 template <bool V4>
 __device__ __forceinline__ void zero_rows(float *base, const int (&pp)[8], int p, unsigned mask, int N, int col, int lane) {
   if (V4) {
-    if (col >= N) return;
+    if (col + (lane & 7) * 4 >= N) return;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + (lane >> 3);
@@ -274,7 +274,7 @@ __device__ void tc_mma(const TcArgs &a, uint32_t smem_base, uint32_t bar_full, u
 #define TCT_LAP(i)
 #endif
 
-template <int DIR, bool V4>   // DIR: 0 = forward, 1 = backward; V4: N is a multiple of 32 (float4 form of the epilogue traffic)
+template <int DIR, bool V4>   // DIR: 0 = forward, 1 = backward; V4: N is a multiple of 4 (float4 form of the epilogue traffic)
 __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
   TCT_DECL;
   extern __shared__ unsigned char smraw[];
@@ -565,7 +565,7 @@ int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bo
     k_rowmax<<<c->sm_count * 8, 256, 0, c->stream>>>(c->E, N, np, c->tc_mrow);
   }
   // (the epilogue addresses points with 32-bit indices relative to the chunk: chunks stay below 2^31 points)
-  auto kf = backward ? (N % 32 == 0 ? k_fb_tc<1, true> : k_fb_tc<1, false>) : (N % 32 == 0 ? k_fb_tc<0, true> : k_fb_tc<0, false>);
+  auto kf = backward ? (N % 4 == 0 ? k_fb_tc<1, true> : k_fb_tc<1, false>) : (N % 4 == 0 ? k_fb_tc<0, true> : k_fb_tc<0, false>);
   cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kf<<<grid, TC_THREADS, smem, c->stream>>>(a);
   return DNBC_OK;

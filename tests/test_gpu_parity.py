@@ -520,11 +520,11 @@ def test_bridge_clamped_em_reproduces_supervised_learner(oracle):
     np.testing.assert_allclose(p["var"], sup.var, rtol=1e-4)
 
 
-@pytest.mark.parametrize("N", [65, 96, 100, 128, 160, 192, 200, 288, 320, 352, 448, 500])
+@pytest.mark.parametrize("N", [65, 96, 100, 128, 131, 160, 192, 200, 288, 320, 352, 399, 448, 500])
 def test_tensor_core_recursion_any_state_count(oracle, N):
     """Every state count from 65 to 512 runs the tcgen05 recursions on a multiple-of-64 padding (k_tc.cu: K blocks of 64
     source states, a last accumulator block of 64 / 128 / 192 columns, 32-column chunks of padding masked off in the
-    coalesced epilogue when N is a multiple of 32, row-strided epilogue otherwise): statistics, posteriors and two EM
+    float4 form of the coalesced epilogue when N is a multiple of 4 with padded slots masked off, lane-per-column form otherwise): statistics, posteriors and two EM
     iterations against the fp64 oracle over two 128-sequence batches of ragged lengths."""
     m = random_model(oracle, N, [5], [2], 900 + N, transitions_per_state=min(N, 48))
     rng = np.random.default_rng(901 + N)
