@@ -1,5 +1,6 @@
-// k_stats2.cu -- K3 statistics sweep, second generation, for state counts that are a multiple of 32
-// (the scale-out shape N = 64 and the large-state shape N = 512).
+// k_stats2.cu -- K3 statistics sweep, second generation, for state counts from 32 up that are a multiple of 4
+// (the scale-out shape N = 64, the large-state shape N = 512; a last slice of fewer than 32 states idles its spare
+// lanes on zero posteriors) and, in a grouped layout, for 8 <= N < 32.
 //
 // Same mathematics and the same fp32-window / fp64-flush scheme as k_stats_pk (k_mixture.cu): GMM
 // responsibilities and moments (generalising the E- and M-step sums of EM1D.run,
@@ -279,15 +280,17 @@ constexpr int PGMAX = 4;         // points per warp step in the grouped layout (
 //              the [32 points][32 states] slice of GA.
 // GRP = true : N <= 32; lane = (point slot gi, state lj), a block is 32 steps of PG points, the tile is the contiguous
 //              [32 PG points][N] piece of GA.  Lanes past the last whole group and padded states carry zero weight.
-template <int KP, bool ODD, bool GRP>
+// PART (!GRP only): N is not a multiple of 32 and the last slice has idle lanes (a template flag: carrying the two
+// predicates through the hot loop of the full-slice kernel cost it 3 % at the scale-out shape).
+template <int KP, bool ODD, bool GRP, bool PART>
 __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.dm.N, D = a.dm.D, C = a.dm.C, Vmax = a.dm.Vmax, Kmax = a.dm.Kmax, Npad = a.dm.Npad;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int LG = GRP ? a.LG : 32, PG = GRP ? a.PG : 1;
   const int gi = GRP ? lane / LG : 0, lj = GRP ? lane % LG : lane;
-  const bool lane_on = !GRP || (gi < PG && lj < N);
-  const int j = GRP ? (lane_on ? lj : 0) : blockIdx.y * 32 + lane;   // a real state
+  const bool lane_on = GRP ? (gi < PG && lj < N) : (!PART || (int)blockIdx.y * 32 + lane < N);
+  const int j = lane_on ? (GRP ? lj : blockIdx.y * 32 + lane) : 0;   // a real state
   const int u = blockIdx.z * a.nw + w;                      // this warp's variable index
   const bool has_c = u < C, has_d = u < D;
   if (!has_c && !has_d) return;
@@ -373,8 +376,16 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
 
   // posterior tile of a block.  !GRP: lane l copies, for i = 0..7, the 16 bytes of point 4 i + l / 8, states
   // 4 (l % 8) .. + 3 of this slice.  GRP: the tile is one contiguous piece of GA.
+  // A slot of four states past N (last slice of a state count that is not a multiple of 32; N is a multiple of 4,
+  // so a slot is all states or all padding) is never copied: it keeps the zeros written here, and its lanes
+  // accumulate nothing (weight 0 against coefficients without mass).
+  const bool slot_on = GRP || !PART || (int)blockIdx.y * 32 + (lane & 7) * 4 < N;
   const float *gsrc0 = a.GA + (int64_t)(lane >> 3) * N + blockIdx.y * 32 + (lane & 7) * 4;
   float *gdst0 = gtile + (lane >> 3) * 32 + (lane & 7) * 4;
+  if (!GRP && PART && !slot_on) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) *reinterpret_cast<float4 *>(gdst0 + (i >> 3) * 1024 + (i & 7) * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   auto issue_tile = [&](int blk, int stage) {
     if (GRP) {
       const float *src = a.GA + (int64_t)blk * tile_floats;
@@ -383,8 +394,10 @@ __global__ void __maxnreg__(S2_MAXREG) k_stats2(Stat2Args a) {
     } else {
       const float *src = gsrc0 + (int64_t)blk * 32 * N;
       float *dst = gdst0 + stage * 1024;
+      if (slot_on) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cp_async16(dst + i * 128, src + (int64_t)i * 4 * N);
+        for (int i = 0; i < 8; ++i) cp_async16(dst + i * 128, src + (int64_t)i * 4 * N);
+      }
     }
     cp_async_commit();
   };
@@ -524,7 +537,7 @@ bool stats2_supported(const dnbc_ctx *c) {
   const Dims &d = c->dm;
   const int units = d.C > d.D ? d.C : d.D;
   if (d.Kmax > 8 || units < 1) return false;
-  if (d.N % 32 == 0) return stats2_smem(d, NW_MAX, false) <= 110 * 1024;
+  if (d.N >= 32 && d.N % 4 == 0) return stats2_smem(d, NW_MAX, false) <= 110 * 1024;   // (rows of 16-byte aligned posterior slots)
   return d.N >= 8 && d.N < 32 && stats2_smem(d, NW_MAX, true) <= 110 * 1024;
 }
 
@@ -532,7 +545,7 @@ bool stats2_supported(const dnbc_ctx *c) {
 // covered (the caller gives the rest to k_stats_pk)
 int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
   const Dims &d = c->dm;
-  const bool grp = d.N % 32 != 0;
+  const bool grp = d.N < 32, part = !grp && d.N % 32 != 0;
   int LG = 32, PG = 1;
   if (grp) group_shape(d, LG, PG);
   const int TPB = 32 * PG;
@@ -542,7 +555,7 @@ int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
   const int units = d.C > d.D ? d.C : d.D;
   // 16 warps per SM at <= 128 registers: CTAs of nw warps, e.g. 3 x 5 warps when there are 5 variables
   const int nw = units > NW_MAX ? NW_MAX : units;
-  const int gz = (units + nw - 1) / nw, gy = grp ? 1 : d.N / 32;
+  const int gz = (units + nw - 1) / nw, gy = grp ? 1 : (d.N + 31) / 32;
   Stat2Args a{d, c->tables(), c->data(), p0, (int)nblk, c->GA, c->d_mu, c->d_stats + sl.gmm, c->d_stats + sl.cat,
               c->d_stats + sl.gamma, 4096, nw, LG, PG};
   const size_t smem = stats2_smem(d, nw, grp);
@@ -558,8 +571,9 @@ int64_t launch_stats2(dnbc_ctx *c, int64_t p0, int64_t np) {
   const int KP = odd ? d.Kmax / 2 : (d.Kmax + 1) / 2;
 #define STATS2_LAUNCH(KP_, ODD_, GRP_)                                                                            \
   do {                                                                                                            \
-    cudaFuncSetAttribute(k_stats2<KP_, ODD_, GRP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    k_stats2<KP_, ODD_, GRP_><<<grid, nw * 32, smem, c->stream>>>(a);                                              \
+    auto kf = (!GRP_ && part) ? k_stats2<KP_, ODD_, GRP_, !GRP_> : k_stats2<KP_, ODD_, GRP_, false>;              \
+    cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
+    kf<<<grid, nw * 32, smem, c->stream>>>(a);                                                                    \
   } while (0)
 #define STATS2_CASE(KP_)                                                                                          \
   if (KP == KP_) {                                                                                                \

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU call AC: k_xi_tc with free off-items (partial tiles): parity tests and timings at in-between state counts
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "tensor_core or large_state or estep_statistics or dispatch" > gpurun_out/ac_pytest.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x  > gpurun_out/ac_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/ac_pytest.log; tail -3 gpurun_out/ac_pytest.log
 rm -f gpurun_out/ac_kbench.jsonl
 for w in "custom:N=100,T=200 50000" "custom:N=200,T=200 25000" "custom:N=300,T=200 12500" "custom:N=320,T=200 12500" "custom:N=500,T=200 12500" "largeN 12500" "scaleout 8000"; do
