@@ -39,6 +39,9 @@ constexpr int A_TILE = TC_M * TC_KB * 2;    // 16 KB
 constexpr int B_TILE = TC_NH * TC_KB * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;   // hi + lo of both operands: 96 KB
 constexpr uint32_t BULK = 16 * 1024;        // bytes per bulk copy
+#ifndef TC_BWD_PFE
+#define TC_BWD_PFE 1
+#endif
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -160,6 +163,24 @@ __device__ __forceinline__ void zero_rows(float *base, const int (&pp)[8], int p
     for (int it = 0; it < 32; ++it) {
       const int pr = __shfl_sync(FULL, p, it);
       if (con && ((mask >> it) & 1u)) base[(int64_t)pr * N + col + lane] = 0.f;
+    }
+  }
+}
+// pull columns col .. col+31 of the rows selected by mask into L2 (no registers): one request per 128-byte line
+template <bool V4>
+__device__ __forceinline__ void chunk_prefetch_l2(const float *base, const int (&pp)[8], int p, unsigned mask, int N, int col, int lane) {
+  if (V4) {
+    if (col + (lane & 7) * 4 >= N || (lane & 7) != 0) mask = 0u;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      if ((mask >> rr) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)pp[it] * N + col));
+    }
+  } else {
+    if (col < N && ((mask >> lane) & 1u)) {                  // lane = row: the chunk's first and last byte (at most two lines)
+      const float *r0 = base + (int64_t)p * N + col;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + (col + 31 < N ? 31 : N - 1 - col)));
     }
   }
 }
@@ -404,6 +425,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
           float d[32], al[32];
           chunk_to_rows<V4>(tb, lane, qa, al);
           if (ch + 1 < ncol / 32) chunk_ldg<false, V4>(a.AL, pp, pi32, lmask, N, c0 + 32, lane, 0.f, qa);
+#if TC_BWD_PFE
+          chunk_prefetch_l2<V4>(a.E, pp, pi32, lmask, N, c0, lane);   // the second pass finds its emission rows in L2
+#endif
           if (k > 0) tmem_ld32(trow + c0, d);
           else {
 #pragma unroll
