@@ -39,6 +39,9 @@ constexpr int A_TILE = TC_M * TC_KB * 2;    // 16 KB
 constexpr int B_TILE = TC_NH * TC_KB * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;   // hi + lo of both operands: 96 KB
 constexpr uint32_t BULK = 16 * 1024;        // bytes per bulk copy
+#ifndef TC_FWD_PFE
+#define TC_FWD_PFE 1
+#endif
 #ifndef TC_BWD_PFE
 #define TC_BWD_PFE 1
 #endif
@@ -370,6 +373,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_fb_tc(TcArgs a) {
         float sum = 0.f;
         float en[32];
         chunk_ldg<true, V4>(a.E, pp, pi32, lmask, N, col0, lane, -INFINITY, en);
+#if TC_FWD_PFE
+        for (int ch = 1; ch < ncol / 32; ++ch) chunk_prefetch_l2<V4>(a.E, pp, pi32, lmask, N, col0 + ch * 32, lane);
+#endif
         if (k > 0) { mbar_wait(my_done, gsteps & 1); tc_fence_after(); }
         TCT_LAP(0);
         for (int ch = 0; ch < ncol / 32; ++ch) {

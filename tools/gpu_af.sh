@@ -6,7 +6,7 @@ timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "tensor_co
 echo "pytest rc=$?" >> gpurun_out/af_pytest.log; tail -3 gpurun_out/af_pytest.log
 echo skip-fuzz > gpurun_out/af_fuzz.txt
 rm -f gpurun_out/af_kbench.jsonl
-for w in "largeN 12500" "custom:N=128,T=200 50000" "custom:N=300,T=200 12500"; do
+for w in "largeN 100000" "custom:N=200,T=200 100000"; do
   for lib in "" build/libdnbc_nopfe.so; do
     DNBC_B200_LIB=$lib timeout 300 python tools/kbench.py $w 2 >> gpurun_out/af_kbench.jsonl 2>> gpurun_out/af_err.log
   done
