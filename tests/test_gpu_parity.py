@@ -550,7 +550,8 @@ def test_tensor_core_recursion_any_state_count(oracle, N):
 
 
 def test_large_state_space_kernels(oracle):
-    """N = 300 (padded to 512) exercises the CTA-per-sequence recursions."""
+    """N = 300: tcgen05 recursions on operands padded to 320 (float4 epilogue, a last accumulator block of 64 columns),
+    tcgen05 transition statistics with partial tiles, k_stats2 with a partial last slice, max-plus Viterbi tiles padded to 512."""
     m = random_model(oracle, 300, [6], [2], 81, transitions_per_state=40)
     data = sample(oracle, m, [30, 12, 1, 25], 82)
     q = perturb(oracle, m, 83)
