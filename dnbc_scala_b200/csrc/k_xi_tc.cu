@@ -24,9 +24,6 @@
 
 namespace {
 
-#ifndef XI_PF2
-#define XI_PF2 0
-#endif
 constexpr int XT = 256;     // threads per CTA
 constexpr int XKB = 64;     // points per K block = one 128-byte swizzled row of bf16
 constexpr int XWIN = 8;     // K blocks accumulated in TMEM before the window is folded into registers
@@ -87,14 +84,6 @@ __device__ __forceinline__ void load_item(const Item &it, const float *__restric
   } else {
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = it.k0 + k < left ? __ldg(g + (int64_t)k * N) : 0.f;
-  }
-}
-// request the 8 rows of an item's chunk into L2 (one lane per 128-byte line; no registers)
-__device__ __forceinline__ void prefetch_item(const Item &it, const float *__restrict__ blk, int N, int lane) {
-  if (lane == 0) {
-    const float *g = blk + it.g;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (int64_t)k * N));
   }
 }
 __device__ __forceinline__ void store_item(const Item &it, uint32_t tile_hi, uint32_t tile_lo, const float (&x)[8]) {
@@ -191,14 +180,6 @@ __global__ void __launch_bounds__(XT, NJ == 64 ? DNBC_XI_OCC : 1) k_xi_tc(XiArgs
 #pragma unroll
         for (int n = 0; n < IB; ++n) load_item(ib[n], a.U + (p + XKB) * N, N, pe - p - XKB, xb[n]);
       }
-#if XI_PF2
-      if (NJ > 64 && p + 3 * XKB <= pe) {                     // and the block after it is requested into L2
-#pragma unroll
-        for (int n = 0; n < IA; ++n) prefetch_item(ia[n], a.AL + (p + 2 * XKB) * N, N, lane);
-#pragma unroll
-        for (int n = 0; n < IB; ++n) prefetch_item(ib[n], a.U + (p + 2 * XKB) * N, N, lane);
-      }
-#endif
     } else {
 #pragma unroll
       for (int n = 0; n < IA; ++n) {
