@@ -365,19 +365,28 @@ static size_t vt_smem(int NP) {
 }
 // (the two delta buffers of 32 sequences are 8 NP x 32 bytes: padded state counts above 512 do not fit one SM's shared
 // memory and stay on k_decode_block; a third stage of the ln A ring was measured slower, 647 vs 608 ms)
-bool viterbi_tile_supported(const dnbc_ctx *c) {
-  return c->dm.Npad >= VT_JC && c->dm.Npad % VT_JC == 0 && vt_smem(c->dm.Npad) <= 227 * 1024;
+// padded state count of the tiles: a multiple of the 256 destinations of a pass (65 .. 128 states run padded to 256 as
+// well: the lane-group kernel of k_decode.cu that used to take them is slower); 0 = not supported
+#ifndef VT_MIN_N
+#define VT_MIN_N 65
+#endif
+static int vt_np(const dnbc_ctx *c) {
+  const int N = c->dm.N;
+  if (N < VT_MIN_N) return 0;
+  const int NP = (N + VT_JC - 1) / VT_JC * VT_JC;
+  return vt_smem(NP) <= 227 * 1024 ? NP : 0;
 }
+bool viterbi_tile_supported(const dnbc_ctx *c) { return vt_np(c) != 0; }
 
 int launch_viterbi_tile(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const float *E, uint16_t *path, double *score,
                         uint8_t *tie, uint16_t *bp) {
-  const int N = c->dm.N, NP = c->dm.Npad;
+  const int N = c->dm.N, NP = vt_np(c);
   if (!c->vt_logA) {                                         // [NP][NP] padded ln A, then its row maxima and minima
     if (cudaMalloc((void **)&c->vt_logA, ((size_t)NP * NP + 2 * NP) * sizeof(float)) != cudaSuccess) return DNBC_ENOMEM;
   }
   float *rowmax = c->vt_logA + (size_t)NP * NP, *rowmin = rowmax + NP;
   c->launches += 2;
-  k_pad_logA<<<c->sm_count * 2, 256, 0, c->stream>>>(c->t_logA, NP, c->d_active, N, NP, c->vt_logA);
+  k_pad_logA<<<c->sm_count * 2, 256, 0, c->stream>>>(c->t_logA, c->dm.Npad, c->d_active, N, NP, c->vt_logA);
   k_row_extrema<<<(NP * 32 + 255) / 256, 256, 0, c->stream>>>(c->vt_logA, c->d_active, N, NP, rowmax, rowmin);
   VtArgs a{N, NP, c->d_off, s0, s1, p0, E, c->t_logpi, c->vt_logA, rowmax, rowmin, c->d_active, path, score, tie, bp};
   const size_t smem = vt_smem(NP);
