@@ -421,6 +421,14 @@ extern "C" int dnbc_data_shape(const dnbc_ctx *c, int64_t *n_seq, int64_t *n_poi
 // ---------------------------------------------------------------------------------
 struct Chunk { int64_t s0, s1, p0, np; };
 
+// tensor-core recursions (65 .. 512 states): a chunk that is not the last one ends on a whole number of waves of
+// 128-sequence batches (k_tc.cu: fb_tc_wave_sequences)
+static int64_t whole_waves(const dnbc_ctx *c, int64_t s, int64_t e) {
+  const int64_t wave = fb_tc_wave_sequences(c);
+  if (wave <= 0 || e >= c->S || e - s < wave) return e;
+  return s + (e - s) / wave * wave;
+}
+
 static std::vector<Chunk> make_chunks(const dnbc_ctx *c, int64_t max_points) {
   std::vector<Chunk> out;
   int64_t s = 0;
@@ -431,6 +439,7 @@ static std::vector<Chunk> make_chunks(const dnbc_ctx *c, int64_t max_points) {
     e = std::upper_bound(c->h_off.begin() + s + 1, c->h_off.end(), p0 + max_points) - c->h_off.begin() - 1;
     if (e <= s) e = s + 1;
     if (e > c->S) e = c->S;
+    e = whole_waves(c, s, e);
     out.push_back(Chunk{s, e, p0, c->h_off[e] - p0});
     s = e;
   }
@@ -448,6 +457,7 @@ static std::vector<Chunk> make_chunks_progressive(const dnbc_ctx *c, int64_t fir
     int64_t e = std::upper_bound(c->h_off.begin() + s + 1, c->h_off.end(), p0 + want) - c->h_off.begin() - 1;
     if (e <= s) e = s + 1;
     if (e > c->S) e = c->S;
+    e = whole_waves(c, s, e);
     out.push_back(Chunk{s, e, p0, c->h_off[e] - p0});
     s = e;
     want = std::min(want * 2, max_points);

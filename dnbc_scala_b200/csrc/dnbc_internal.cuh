@@ -203,6 +203,7 @@ void launch_backtrace(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, const uin
 bool xi_tc_supported(const dnbc_ctx *c);
 void launch_xi_tc(dnbc_ctx *c, int64_t np);
 bool fb_tc_supported(const dnbc_ctx *c);
+int64_t fb_tc_wave_sequences(const dnbc_ctx *c);
 void launch_tc_tables(dnbc_ctx *c);
 int launch_fb_tc(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, int64_t np, bool backward);
 void launch_fb_block(dnbc_ctx *c, int64_t s0, int64_t s1, int64_t p0, bool backward);

@@ -557,6 +557,10 @@ static int tc_np(const dnbc_ctx *c) {
 static size_t tc_table_bytes(int NP) { return (size_t)((NP + TC_NH - 1) / TC_NH) * (NP / TC_KB) * (2 * B_TILE); }
 
 bool fb_tc_supported(const dnbc_ctx *c) { return tc_np(c) != 0; }
+// sequences one wave of the recursion covers (one 128-sequence batch per SM): chunks of the E-step are cut at whole
+// multiples of it -- a batch costs the same whether all of its rows are live or not, and a chunk of 1.65 waves (what
+// the scratch budget gives at N = 512, T = 200) takes the time of two
+int64_t fb_tc_wave_sequences(const dnbc_ctx *c) { return tc_np(c) != 0 ? (int64_t)c->sm_count * TC_M : 0; }
 
 void launch_tc_tables(dnbc_ctx *c) {
   const int NP = tc_np(c);
