@@ -823,7 +823,7 @@ bool mixture_emission_fast(const dnbc_ctx *c) {
 }
 template <int KU, bool BIGP = false>
 static void launch_emit_px_t(dnbc_ctx *c, const EmitArgs &a, dim3 grid, size_t smem) {
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_emission_px<KU, BIGP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 32 * 1024) cudaFuncSetAttribute(k_emission_px<KU, BIGP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // (static + dynamic shared memory count against the 48 KB default: opt in with room to spare)
   k_emission_px<KU, BIGP><<<grid, PX_WARPS * 32, smem, c->stream>>>(a);
 }
 
@@ -908,7 +908,7 @@ static void launch_stats_pk(dnbc_ctx *c, int64_t p0, int64_t np, const float *GA
   const int KP = (d.Kmax + 1) / 2;
 #define STATS_CASE(KP_)                                                                                              \
   if (KP == KP_) {                                                                                                   \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_stats_pk<KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (smem > 32 * 1024) cudaFuncSetAttribute(k_stats_pk<KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     k_stats_pk<KP_><<<grid, NW * 32, smem, c->stream>>>(a);                                                          \
     return;                                                                                                          \
   }

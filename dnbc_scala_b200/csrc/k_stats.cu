@@ -197,7 +197,7 @@ void launch_stats_cat(dnbc_ctx *c, int64_t p0, int64_t np) {
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   const size_t smem = (size_t)tpb * c->dm.Vmax * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_stats_cat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 32 * 1024) cudaFuncSetAttribute(k_stats_cat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_stats_cat<<<dim3((unsigned)gx, gy), tpb, smem, c->stream>>>(c->dm, c->data(), p0, np, c->GA, c->d_stats + sl.cat,
                                                                 c->d_stats + sl.gamma, window);
 }

@@ -22,6 +22,9 @@ def flagged_or_equal(path, opath, tie, otie, off, backtrace):
     return all(flagged[off[s]:(off[s + 1] if backtrace else n + 1)].any() for n, s in zip(diff, seq_of))
 
 
+LAST = {"tag": ""}        # the case in flight, printed when anything raises
+
+
 def one(case, rng, large=False):
     N = int(rng.choice([100, 192, 256, 300, 400, 512] if large else
                        [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 17, 31, 32, 33, 48, 63, 64, 65, 70, 96, 100, 128, 130, 160, 200, 256, 300, 320]))
@@ -43,6 +46,7 @@ def one(case, rng, large=False):
     data = sample(oracle, m, lengths, int(rng.integers(1 << 30)))
     q = perturb(oracle, m, int(rng.integers(1 << 30)))
     tag = f"case {case}: N={N} V={V} K={K} tps={tps} lengths={lengths[:8]}... P={data.P}"
+    LAST["tag"] = tag + f" all lengths={lengths}"
     want = oracle.estep(q, data)
     if not np.isfinite(want).all():
         return None          # a zero-probability sequence: outside the parity contract
@@ -162,7 +166,12 @@ def main():
     large = len(sys.argv) > 3 and sys.argv[3] == "large"
     done = skipped = 0
     for case in range(cases):
-        if one(case, rng, large) is None:
+        try:
+            res = one(case, rng, large)
+        except Exception:
+            print("FAILED", LAST["tag"], flush=True)
+            raise
+        if res is None:
             skipped += 1
         else:
             done += 1

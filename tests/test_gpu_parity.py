@@ -549,6 +549,29 @@ def test_tensor_core_recursion_any_state_count(oracle, N):
     np.testing.assert_allclose(ll, ll_want, rtol=TOL)
 
 
+def test_emission_with_exactly_48k_of_dynamic_shared_memory(oracle):
+    """N = 1, two discrete + two continuous variables, Kmax = 6: the points-packed emission kernel asks for exactly
+    49,152 bytes of dynamic shared memory, which together with its static bytes is past the 48 KB a kernel gets
+    without opting in (found by tests/fuzz_parity.py, seed 9001 case 190: `invalid argument` at the launch)."""
+    m = random_model(oracle, 1, [4, 7], [1, 6], 190, transitions_per_state=1)
+    lengths = [1, 0, 0, 1, 1, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 1, 1, 0, 1]
+    data = sample(oracle, m, lengths, 191)
+    q = perturb(oracle, m, 192)
+    want = oracle.estep(q, data)
+    with ctx_for(nat, q) as ctx:
+        ctx.set_option(nat.OPT_FUSED_ESTEP, 2)               # the general pipeline (the single-launch E-step has no emission kernel)
+        upload(ctx, data, labels=False)
+        e = ctx.emission_logprob(nat.PREC_F32)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        g = ctx.em_posteriors()
+    np.testing.assert_allclose(e, oracle.emission_loglik(q, data), rtol=3e-6, atol=3e-5)
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"])
+    np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
+
+
 def test_large_state_space_kernels(oracle):
     """N = 300: tcgen05 recursions on operands padded to 320 (float4 epilogue, a last accumulator block of 64 columns),
     tcgen05 transition statistics with partial tiles, k_stats2 with a partial last slice, max-plus Viterbi tiles padded to 512."""
