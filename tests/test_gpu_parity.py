@@ -572,6 +572,58 @@ def test_emission_with_exactly_48k_of_dynamic_shared_memory(oracle):
     np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=2e-5)
 
 
+EXTREME_SHAPES = [
+    (2, [254], []),                      # the largest alphabet the ABI takes
+    (3, [200] * 12, []),                 # many wide discrete variables
+    (5, [], [8] * 40),                   # many full mixtures
+    (7, [3] * 40, [2] * 40),             # 40 + 40 variables
+    (64, [30] * 3, [32]),                # 32 components: beyond the packed kernels (generic emission / statistics)
+    (33, [100] * 4, [9, 1]),             # 9 components, odd state count above 32
+    (16, [254, 2], [16]),
+    (100, [50] * 6, [8] * 6),            # tensor-core state count with wide variables
+    (600, [], [3]),                      # above 512 states: CTA-per-sequence kernels
+    (1024, [3], [2]),                    # the largest state count the ABI takes
+]
+
+
+@pytest.mark.parametrize("N,V,K", EXTREME_SHAPES)
+def test_extreme_shapes(oracle, N, V, K):
+    """Shapes at the limits of the ABI (dnbc_api.cu:63-79: 1024 states, 254 symbols, 32 components, 255 variables are
+    the caps): every launch configuration has to exist -- tests/fuzz_parity.py draws at most 3 + 3 variables, 11 symbols
+    and 8 components -- and the E-step, the posteriors and all three decoders have to agree with the oracle."""
+    m = random_model(oracle, N, V, K, 7000 + N, transitions_per_state=min(N, 9))
+    rng = np.random.default_rng(7001 + N)
+    lengths = [int(x) for x in rng.integers(0, 13, 11)] + [17]
+    data = sample(oracle, m, lengths, 7002 + N)
+    q = perturb(oracle, m, 7003 + N)
+    want = oracle.estep(q, data)
+    opath, oscore, otie = oracle.decode(q, data, oracle.DECODE_BACKTRACE)
+    rpath, rscore, rtie = oracle.decode(q, data, oracle.DECODE_REFERENCE)
+    with ctx_for(nat, q) as ctx:
+        upload(ctx, data, labels=False)
+        ctx.em_estep()
+        got = ctx.em_get_stats()
+        g = ctx.em_posteriors()
+        p32, s32, t32 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F32)
+        p64, s64, t64 = ctx.decode(nat.DECODE_BACKTRACE, nat.PREC_F64)
+        rp, rs, rt = ctx.decode(nat.DECODE_REFERENCE, nat.PREC_F64)
+        ll = ctx.em_iterate(2)
+    sw, sg = oracle.split_stats(q, want), oracle.split_stats(q, got)
+    assert abs(sg["ll"] - sw["ll"]) <= TOL * abs(sw["ll"]) + 1e-6
+    for key in ("pi", "xi", "gamma", "cat"):
+        np.testing.assert_allclose(sg[key], sw[key], rtol=2e-4, atol=2e-4, err_msg=key)
+    if K:
+        np.testing.assert_allclose(sg["gmm"][..., 0], sw["gmm"][..., 0], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(g, oracle.posteriors(q, data), atol=5e-5)
+    _paths_equal_except_ties(p32, opath, t32, otie, data.off, backtrace=True)
+    _paths_equal_except_ties(p64, opath, t64, otie, data.off, backtrace=True)
+    _paths_equal_except_ties(rp, rpath, rt, rtie, data.off)
+    fin = np.isfinite(oscore)
+    np.testing.assert_allclose(s64[fin], oscore[fin], rtol=1e-11)
+    r = q.copy()
+    np.testing.assert_allclose(ll, oracle.em_iterate(r, data, 2), rtol=TOL)
+
+
 def test_large_state_space_kernels(oracle):
     """N = 300: tcgen05 recursions on operands padded to 320 (float4 epilogue, a last accumulator block of 64 columns),
     tcgen05 transition statistics with partial tiles, k_stats2 with a partial last slice, max-plus Viterbi tiles padded to 512."""
