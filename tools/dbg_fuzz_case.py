@@ -1,3 +1,6 @@
+"""Replays the draws of tests/fuzz_parity.py (FUZZ_LONG=1, seed 9001) up to case 190 -- the N = 1 shape whose emission
+launch failed with `invalid argument` (48 KB of dynamic shared memory without the opt-in) -- and runs the stages of the
+pipeline one by one with CUDA_LAUNCH_BLOCKING=1.  Kept as the template for the next failure the fuzz finds."""
 import os, sys
 os.environ["FUZZ_LONG"] = "1"
 os.environ["CUDA_LAUNCH_BLOCKING"] = "1"
