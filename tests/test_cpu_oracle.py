@@ -297,3 +297,13 @@ def test_library_reads_no_environment():
     for f in os.listdir(csrc):
         if f.endswith((".cu", ".cuh")):
             assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+
+
+def test_custom_workload_names():
+    """tools/kbench.py / dbench.py take ad-hoc shapes ("custom:N=300,T=200") next to the BASELINE configuration names."""
+    from dnbc_scala_b200 import workloads
+    wl = workloads.by_name("custom:N=300,C=2,K=4,T=50")
+    assert (wl.N, wl.C, wl.K, wl.T, wl.D, wl.transitions_per_state) == (300, 2, 4, 50, 5, 300)
+    assert workloads.by_name("scaleout") is workloads.WORKLOADS["scaleout"]
+    p = workloads.true_params(wl)
+    assert p["A"].shape == (300, 300) and np.allclose(p["A"].sum(1), 1.0) and p["mu"].shape == (2, 300, 4)
